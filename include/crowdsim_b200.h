@@ -1,0 +1,187 @@
+/*
+ * include/crowdsim_b200.h -- C ABI of libcrowdsim_b200.so (the drop-in boundary).
+ *
+ * Batched CrowdSim-v0 physics on one B200: B independent environments, N humans each,
+ * stepped in lockstep by hand-written sm_100a kernels. Plain pointers and sizes only; every
+ * pointer is a DEVICE pointer owned by the caller (torch, cudaMalloc, ...), no hidden
+ * allocation, no synchronisation: calls enqueue work on `stream` (a cudaStream_t passed as
+ * void*, NULL = legacy default stream) and return 0, a negative CROWDSIM_E* code for a bad
+ * argument, or a positive cudaError_t.
+ *
+ * What each entry point replaces in the reference (paths relative to /root/reference):
+ *   crowdsim_step            crowd_sim/envs/crowd_sim.py:317-420 (CrowdSim.step, update=True) including the
+ *                            N x Human.act -> ORCA.predict -> rvo2 doStep (crowd_sim/envs/policy/orca.py:82-132),
+ *                            optionally the robot's own ORCA.predict (crowd_nav/utils/explorer.py:42), the
+ *                            per-step part of Explorer.run_k_episodes (explorer.py:41-72)
+ *   crowdsim_orca_act        crowd_sim/envs/utils/robot.py:9-14 with policy ORCA (orca.py:82-132), batched
+ *   crowdsim_reset           crowd_sim/envs/crowd_sim.py:251-312 + generators :155-207 (np.random MT19937)
+ *   crowdsim_lookahead_pack  crowd_nav/policy/multi_human_rl.py:35-45 = 81 x env.onestep_lookahead
+ *                            (crowd_sim.py:314-315,414-416) + CADRL.propagate (cadrl.py:104-129) +
+ *                            CADRL.rotate (cadrl.py:187-222), fused
+ *   crowdsim_pack_joint      crowd_sim/envs/utils/state.py:17-18,36-37 (14-tuple) + cadrl.py:187-222 (rotate)
+ *
+ * Layout in HBM (structure of arrays, float64 like the reference's Python floats):
+ *   two-vectors are interleaved (x,y) pairs so one agent's pair is one 16-byte load;
+ *   human arrays are [B][N][2] (env-major), robot arrays [B][2], scalars [B].
+ */
+#ifndef CROWDSIM_B200_H
+#define CROWDSIM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CROWDSIM_ABI_VERSION 1
+
+/* error codes */
+#define CROWDSIM_OK            0
+#define CROWDSIM_EINVAL       (-1)   /* NULL required pointer / B,N out of range */
+#define CROWDSIM_EUNSUPPORTED (-2)   /* N > CROWDSIM_MAX_HUMANS, max_neighbors > CROWDSIM_MAX_NEIGHBORS, ... */
+#define CROWDSIM_ENODEVICE    (-3)   /* no CUDA device / wrong architecture */
+
+#define CROWDSIM_MAX_HUMANS     63   /* N + 1 (robot) agents of one env are staged together in shared memory */
+#define CROWDSIM_MAX_NEIGHBORS  10   /* orca.py:62 hard-codes max_neighbors = 10 */
+
+/* info codes: crowd_sim/envs/utils/info.py:1-38 */
+#define CROWDSIM_INFO_NOTHING   0
+#define CROWDSIM_INFO_DANGER    1
+#define CROWDSIM_INFO_REACHGOAL 2
+#define CROWDSIM_INFO_COLLISION 3
+#define CROWDSIM_INFO_TIMEOUT   4
+
+/* robot_policy */
+#define CROWDSIM_ROBOT_EXTERNAL_XY  0  /* holonomic ActionXY supplied by the caller (CADRL/LSTM-RL/SARL/Linear) */
+#define CROWDSIM_ROBOT_ORCA         1  /* robot runs ORCA inside the step kernel (test.py --policy orca) */
+#define CROWDSIM_ROBOT_EXTERNAL_ROT 2  /* unicycle ActionRot (v, r) supplied by the caller (agent.py:115-118,133-135) */
+
+/* scenario rules: crowd_sim.py:84-153 */
+#define CROWDSIM_RULE_CIRCLE 0
+#define CROWDSIM_RULE_SQUARE 1
+
+typedef struct crowdsim_params {
+    /* crowd_nav/configs/env.config [env] / [reward]; crowd_sim.py:51-60 */
+    double time_step;                 /* 0.25 */
+    double time_limit;                /* 25   */
+    double success_reward;            /* 1    */
+    double collision_penalty;         /* -0.25 */
+    double discomfort_dist;           /* 0.2  */
+    double discomfort_penalty_factor; /* 0.5  */
+    /* ORCA constants, hard-coded in orca.py:61-64; cast to float32 at the rvo2 boundary */
+    double neighbor_dist;             /* 10 */
+    double time_horizon;              /* 5  */
+    int32_t max_neighbors;            /* 10 */
+    /* orca.py:100-104: radius + 0.01 + safety_space (float64 sum, then cast) */
+    double human_safety_space;        /* 0 */
+    double robot_safety_space;        /* 0 (train.py:121-127 sets 0.15 for IL with an invisible robot) */
+    int32_t robot_visible;            /* env.config [robot] visible; crowd_sim.py:325-327 */
+    int32_t robot_policy;             /* CROWDSIM_ROBOT_* */
+} crowdsim_params;
+
+/* Agent state. Mutable arrays are updated in place by crowdsim_step (agent.py:122-135). */
+typedef struct crowdsim_state {
+    double *h_pos;    /* [B][N][2] human px,py            (mutable) */
+    double *h_vel;    /* [B][N][2] human vx,vy            (mutable) */
+    double *h_goal;   /* [B][N][2] human gx,gy                      */
+    double *h_attr;   /* [B][N][2] human radius, v_pref             */
+    double *r_pos;    /* [B][2]    robot px,py            (mutable) */
+    double *r_vel;    /* [B][2]    robot vx,vy            (mutable) */
+    double *r_goal;   /* [B][2]    robot gx,gy                      */
+    double *r_attr;   /* [B][2]    robot radius, v_pref             */
+    double *r_theta;  /* [B]       robot heading          (mutable, unicycle only) */
+    double *g_time;   /* [B]       env.global_time        (mutable) */
+    uint8_t *active;  /* [B] or NULL: 0 = env frozen (episode over, waiting for reset); NULL = all live */
+} crowdsim_state;
+
+/* Per-step inputs / outputs of crowdsim_step. */
+typedef struct crowdsim_step_io {
+    const double *action; /* [B][2] robot action (vx,vy) or (v,r); ignored (may be NULL) for CROWDSIM_ROBOT_ORCA */
+    double *action_out;   /* [B][2] or NULL: the holonomic velocity actually applied to the robot */
+    double *reward;       /* [B] */
+    double *dmin;         /* [B] min robot-human clearance this step (inf if N == 0) */
+    uint8_t *done;        /* [B] */
+    uint8_t *info;        /* [B] CROWDSIM_INFO_* */
+} crowdsim_step_io;
+
+/*
+ * Episode bookkeeping of Explorer.run_k_episodes (explorer.py:35-72), all optional (pass NULL struct pointer
+ * to skip). Slot arrays are per env slot; result arrays are indexed by the episode's case slot `ep_case[e]`
+ * (0..k-1) and written once when the episode terminates, after which active[e] is cleared (if present).
+ */
+typedef struct crowdsim_episodes {
+    int32_t *ep_case;        /* [B] index into the result arrays, <0 = do not record */
+    int32_t *ep_steps;       /* [B] steps taken so far in the running episode */
+    double  *ep_return;      /* [B] running sum_t discount[t] * reward_t (explorer.py:71-72) */
+    int32_t *ep_too_close;   /* [B] running count of Danger steps (explorer.py:48-49) */
+    double  *ep_min_dist_sum;/* [B] running sum of Danger min_dist (explorer.py:50) */
+    const double *discount;  /* [discount_len] pow(gamma, t*time_step*v_pref), host-computed with C pow */
+    int32_t discount_len;
+    /* results, one row per finished episode */
+    uint8_t *res_info;       /* [k] terminal CROWDSIM_INFO_* */
+    int32_t *res_steps;      /* [k] */
+    double  *res_time;       /* [k] global_time after the terminal step (time_limit for timeouts, explorer.py:62) */
+    double  *res_return;     /* [k] */
+    int32_t *res_too_close;  /* [k] */
+    double  *res_min_dist_sum;/*[k] */
+    double  *res_final_rpos; /* [k][2] or NULL: robot position after the terminal step (parity evidence) */
+} crowdsim_episodes;
+
+/* Scenario generation request for crowdsim_reset. */
+typedef struct crowdsim_reset_args {
+    const uint8_t *mask;     /* [B] or NULL: reset only envs with mask[e] != 0 (NULL = all) */
+    const uint32_t *seed;    /* [B] MT19937 seed per env (crowd_sim.py:272-276: offset[phase] + case) */
+    int32_t rule;            /* CROWDSIM_RULE_* */
+    double circle_radius;    /* env.config [sim] circle_radius = 4 */
+    double square_width;     /* env.config [sim] square_width  = 10 */
+    double human_radius;     /* env.config [humans] radius = 0.3 */
+    double human_v_pref;     /* env.config [humans] v_pref = 1   */
+    double robot_radius;     /* env.config [robot] radius = 0.3  */
+    double robot_v_pref;     /* env.config [robot] v_pref = 1    */
+    double discomfort_dist;  /* 0.2 (min initial separation, crowd_sim.py:168) */
+    int32_t randomize_attributes; /* env.config [env] randomize_attributes (agent.py:39-45) */
+    uint32_t *mt_scratch;    /* [624][B] uint32 device scratch for the MT19937 states (caller-owned) */
+} crowdsim_reset_args;
+
+/* Library / device probing (host only, no kernel launch). */
+int crowdsim_abi_version(void);
+int crowdsim_device_check(int *sm_count, int *cc_major, int *cc_minor);
+/* Kernels launched by this library since load (the bench's gpu_launches claim). */
+unsigned long long crowdsim_launch_count(void);
+
+/* One lockstep env-step for B envs. `ep` may be NULL. */
+int crowdsim_step(const crowdsim_params *prm, int B, int N, crowdsim_state *st, crowdsim_step_io *io,
+                  crowdsim_episodes *ep, void *stream);
+
+/* Robot ORCA action from the current state, no mutation: action_out[B][2]. */
+int crowdsim_orca_act(const crowdsim_params *prm, int B, int N, const crowdsim_state *st, double *action_out,
+                      void *stream);
+
+/* (Re)generate scenarios for the masked envs; also zeroes g_time, velocities, sets theta = pi/2, and,
+ * when `ep` is given, clears the slot accumulators. Sets active[e] = 1 if `st->active` is present. */
+int crowdsim_reset(const crowdsim_reset_args *args, int B, int N, crowdsim_state *st, crowdsim_episodes *ep,
+                   void *stream);
+
+/*
+ * Rotated joint state of the CURRENT state for value-net policies: out[B][N][13] float32
+ * (cadrl.py:187-222 applied to the 14-tuple of state.py:17-18,36-37 after the float32 cast of
+ * multi_human_rl.py:43). kinematics_unicycle selects theta handling (cadrl.py:205-209).
+ */
+int crowdsim_pack_joint(int B, int N, const crowdsim_state *st, int kinematics_unicycle, float *out, void *stream);
+
+/*
+ * One-step lookahead for A candidate robot actions per env (multi_human_rl.py:35-45 with query_env=true):
+ * the N human ORCA solves are done once per env and shared by all A actions. Outputs:
+ *   out_states [B][A][N][13] float32  rotate(next_self_state + next_human_state)
+ *   out_reward [B][A]        float64  reward of step(action, update=False)
+ * actions [A][2] float64 are shared by all envs (CADRL.build_action_space, cadrl.py:82-102).
+ * Nothing is mutated.
+ */
+int crowdsim_lookahead_pack(const crowdsim_params *prm, int B, int N, const crowdsim_state *st,
+                            const double *actions, int A, int kinematics_unicycle,
+                            float *out_states, double *out_reward, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CROWDSIM_B200_H */

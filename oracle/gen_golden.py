@@ -1,0 +1,241 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.json.gz by running the REFERENCE'S OWN PYTHON, unmodified, from /root/reference.
+
+TEST INFRASTRUCTURE. Runs only in the build container (the GPU box has no /root/reference); the JSON
+fixtures it writes are committed and travel. The reference is imported with three shims on sys.path
+(oracle/shims: gym, matplotlib, rvo2); `rvo2` is our float32 restatement of the RVO2 agent step
+(oracle/rvo2_sim.c) because the real Python-RVO2 is an absent, unpinned dependency.
+
+What is recorded (floats as repr() strings, exact round trip):
+  suite_*.json   per test case: terminal info, steps, env.global_time, final robot/human positions,
+                 discounted return (explorer.py:71-72), danger count / min_dist sum, plus the log lines the
+                 reference's Explorer.run_k_episodes prints for the same cases (explorer.py:80-90)
+  traj_*.json    full per-step trajectories of a few cases (every agent position/velocity, reward, info)
+  reset_*.json   initial scenes straight after env.reset (scenario generators + MT19937)
+  rotate.json    CADRL.rotate + one-step lookahead inputs/outputs of MultiHumanRL.predict's inner loop
+
+usage: python oracle/gen_golden.py [--quick]
+"""
+import configparser
+import gzip
+import io
+import json
+import logging
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = '/root/reference'
+sys.path.insert(0, os.path.join(HERE, 'shims'))
+sys.path.insert(0, REF)
+sys.path.insert(0, HERE)
+
+import build as _oracle_build  # noqa: E402
+
+_oracle_build.build()
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import gym  # noqa: E402
+import crowd_sim  # noqa: E402,F401  (registers CrowdSim-v0)
+from crowd_sim.envs.utils.robot import Robot  # noqa: E402
+from crowd_sim.envs.utils.info import Timeout, ReachGoal, Danger, Collision, Nothing  # noqa: E402
+from crowd_sim.envs.utils.action import ActionXY  # noqa: E402
+from crowd_sim.envs.utils.state import JointState  # noqa: E402
+from crowd_sim.envs.policy.orca import ORCA  # noqa: E402
+from crowd_nav.utils.explorer import Explorer  # noqa: E402
+from crowd_nav.policy.policy_factory import policy_factory  # noqa: E402
+
+OUT = os.path.join(ROOT, 'tests', 'golden')
+INFO_CODE = {Nothing: 0, Danger: 1, ReachGoal: 2, Collision: 3, Timeout: 4}
+
+
+def R(x):
+    return repr(float(x))
+
+
+def make_env(human_num=5, test_sim='circle_crossing', robot_visible=False, randomize=False, policy_name='orca',
+             policy_config=None):
+    cfg = configparser.RawConfigParser()
+    cfg.read(os.path.join(REF, 'crowd_nav', 'configs', 'env.config'))
+    cfg.set('sim', 'human_num', str(human_num))
+    cfg.set('robot', 'visible', 'true' if robot_visible else 'false')
+    cfg.set('env', 'randomize_attributes', 'true' if randomize else 'false')
+    env = gym.make('CrowdSim-v0')
+    env.configure(cfg)
+    env.test_sim = test_sim
+    robot = Robot(cfg, 'robot')
+    policy = policy_factory[policy_name]()
+    if policy_config is not None:
+        policy.configure(policy_config)
+    else:
+        policy.configure(cfg)
+    robot.set_policy(policy)
+    env.set_robot(robot)
+    policy.set_phase('test')
+    policy.set_device(torch.device('cpu'))
+    policy.set_env(env)
+    if isinstance(policy, ORCA):
+        policy.safety_space = 0
+    return env, robot, cfg
+
+
+def scene(env):
+    r = env.robot
+    return {
+        'robot': [R(r.px), R(r.py), R(r.vx), R(r.vy), R(r.gx), R(r.gy), R(r.radius), R(r.v_pref), R(r.theta)],
+        'humans': [[R(h.px), R(h.py), R(h.vx), R(h.vy), R(h.gx), R(h.gy), R(h.radius), R(h.v_pref)] for h in env.humans],
+    }
+
+
+def run_suite(name, cases, phase='test', gamma=0.9, record_traj=(), **kw):
+    env, robot, _ = make_env(**kw)
+    # 1) the reference's own Explorer, capturing its log lines
+    stream = io.StringIO()
+    handler = logging.StreamHandler(stream)
+    handler.setFormatter(logging.Formatter('%(message)s'))
+    root = logging.getLogger()
+    root.addHandler(handler)
+    root.setLevel(logging.INFO)
+    explorer = Explorer(env, robot, torch.device('cpu'), gamma=gamma)
+    env.case_counter[phase] = cases[0]
+    explorer.run_k_episodes(len(cases), phase, print_failure=True)
+    root.removeHandler(handler)
+    log_lines = [l for l in stream.getvalue().splitlines() if l]
+
+    # 2) the same episodes again through reset/act/step, recording per-case details
+    env, robot, _ = make_env(**kw)
+    per_case = []
+    trajs = {}
+    total_steps = 0
+    for case in cases:
+        ob = env.reset(phase, case)
+        init = scene(env)
+        done = False
+        rewards = []
+        too_close = 0
+        min_dist_sum = 0.0
+        steps = []
+        while not done:
+            action = robot.act(ob)
+            pre = scene(env) if case in record_traj else None
+            ob, reward, done, info = env.step(action)
+            rewards.append(reward)
+            if isinstance(info, Danger):
+                too_close += 1
+                min_dist_sum += info.min_dist
+            if case in record_traj:
+                steps.append({'pre': pre, 'action': [R(action.vx), R(action.vy)], 'reward': R(reward),
+                              'done': bool(done), 'info': INFO_CODE[type(info)],
+                              'dmin': R(info.min_dist) if isinstance(info, Danger) else None,
+                              'post': scene(env), 'global_time': R(env.global_time)})
+        ret = sum([pow(gamma, t * robot.time_step * robot.v_pref) * r for t, r in enumerate(rewards)])
+        total_steps += len(rewards)
+        per_case.append({'case': case, 'info': INFO_CODE[type(info)], 'steps': len(rewards),
+                         'global_time': R(env.global_time), 'return': R(ret), 'too_close': too_close,
+                         'min_dist_sum': R(min_dist_sum), 'final': scene(env), 'init': init})
+        if case in record_traj:
+            trajs[str(case)] = steps
+    counts = {k: sum(1 for c in per_case if c['info'] == v) for k, v in
+              (('success', 2), ('collision', 3), ('timeout', 4))}
+    out = {'name': name, 'phase': phase, 'config': {k: (v if not isinstance(v, bool) else v) for k, v in kw.items()},
+           'gamma': gamma, 'log_lines': log_lines, 'counts': counts, 'total_env_steps': total_steps,
+           'cases': per_case}
+    with gzip.open(os.path.join(OUT, 'suite_%s.json.gz' % name), 'wt') as f:
+        json.dump(out, f, separators=(',', ':'))
+    if trajs:
+        with gzip.open(os.path.join(OUT, 'traj_%s.json.gz' % name), 'wt') as f:
+            json.dump({'name': name, 'config': kw, 'trajectories': trajs}, f, separators=(',', ':'))
+    print(name, counts, 'env-steps', total_steps)
+    for l in log_lines:
+        print('   ', l)
+    return out
+
+
+def run_resets():
+    """Initial scenes only: scenario generators + MT19937 (crowd_sim.py:155-207, 251-312)."""
+    out = {}
+    for name, kw, phase, cases in [
+        ('circle5_test', dict(human_num=5, test_sim='circle_crossing'), 'test', list(range(0, 40))),
+        ('square5_test', dict(human_num=5, test_sim='square_crossing'), 'test', list(range(0, 40))),
+        ('square20_test', dict(human_num=20, test_sim='square_crossing'), 'test', list(range(0, 20))),
+        ('circle10_test', dict(human_num=10, test_sim='circle_crossing'), 'test', list(range(0, 20))),
+        ('circle5_random_attr', dict(human_num=5, test_sim='circle_crossing', randomize=True), 'test', list(range(0, 20))),
+        ('square5_random_attr', dict(human_num=5, test_sim='square_crossing', randomize=True), 'test', list(range(0, 20))),
+        ('circle5_train', dict(human_num=5, test_sim='circle_crossing'), 'train', [0, 1, 2, 1000, 123456, 4294965294]),
+        ('circle5_val', dict(human_num=5, test_sim='circle_crossing'), 'val', [0, 1, 99]),
+    ]:
+        env, robot, _ = make_env(**kw)
+        robot.policy.multiagent_training = True     # ORCA leaves it None; train/val then use human_num (crowd_sim.py:278)
+        rows = []
+        for c in cases:
+            env.reset(phase, c)
+            offset = {'train': 2000, 'val': 0, 'test': 1000}[phase]
+            rows.append({'case': c, 'seed': offset + c, 'scene': scene(env)})
+        out[name] = {'config': kw, 'phase': phase, 'rows': rows}
+    with gzip.open(os.path.join(OUT, 'reset_scenes.json.gz'), 'wt') as f:
+        json.dump(out, f, separators=(',', ':'))
+    print('reset scenes written')
+
+
+def run_rotate():
+    """CADRL.rotate and the inner loop of MultiHumanRL.predict (multi_human_rl.py:35-45), reference code only."""
+    pcfg = configparser.RawConfigParser()
+    pcfg.read(os.path.join(REF, 'crowd_nav', 'configs', 'policy.config'))
+    torch.manual_seed(0)
+    env, robot, _ = make_env(human_num=5, test_sim='circle_crossing', policy_name='sarl', policy_config=pcfg)
+    policy = robot.policy
+    rows = []
+    for case in (0, 3, 7):
+        ob = env.reset('test', case)
+        orca_robot = ORCA()
+        orca_robot.time_step = env.time_step
+        for step in range(12):
+            state = JointState(robot.get_full_state(), ob)
+            if policy.action_space is None:
+                policy.build_action_space(state.self_state.v_pref)
+            if step % 4 == 0:
+                per_action = []
+                for action in policy.action_space:
+                    next_self_state = policy.propagate(state.self_state, action)
+                    next_human_states, reward, done, info = env.onestep_lookahead(action)
+                    batch = torch.cat([torch.Tensor([next_self_state + nhs]) for nhs in next_human_states], dim=0)
+                    rot = policy.rotate(batch)
+                    per_action.append({'action': [R(action.vx), R(action.vy)], 'reward': R(reward),
+                                       'rotated': [[R(v) for v in row] for row in rot.tolist()]})
+                cur = torch.cat([torch.Tensor([state.self_state + hs]) for hs in state.human_states], dim=0)
+                rows.append({'case': case, 'step': step, 'scene': scene(env), 'global_time': R(env.global_time),
+                             'rotated_current': [[R(v) for v in row] for row in policy.rotate(cur).tolist()],
+                             'lookahead': per_action})
+            # drive the robot with ORCA so the scene evolves through interesting states
+            action = orca_robot.predict(state)
+            ob, reward, done, info = env.step(ActionXY(action.vx, action.vy))
+            if done:
+                break
+    space = [[R(a.vx), R(a.vy)] for a in policy.action_space]
+    with gzip.open(os.path.join(OUT, 'rotate_lookahead.json.gz'), 'wt') as f:
+        json.dump({'action_space': space, 'rows': rows}, f, separators=(',', ':'))
+    print('rotate/lookahead rows', len(rows))
+
+
+def main():
+    quick = '--quick' in sys.argv
+    os.makedirs(OUT, exist_ok=True)
+    n = 50 if quick else 500
+    run_suite('circle5_invisible', list(range(n)), human_num=5, test_sim='circle_crossing', record_traj=(0, 3, 118))
+    run_suite('square5_invisible', list(range(n)), human_num=5, test_sim='square_crossing', record_traj=(0, 192))
+    run_suite('square20_invisible', list(range(20 if quick else 100)), human_num=20, test_sim='square_crossing',
+              record_traj=(0, 61))
+    run_suite('circle5_visible', list(range(n)), human_num=5, test_sim='circle_crossing', robot_visible=True,
+              record_traj=(1,))
+    run_suite('circle10_visible', list(range(20 if quick else 100)), human_num=10, test_sim='circle_crossing',
+              robot_visible=True)
+    run_suite('circle5_random_attr', list(range(20 if quick else 100)), human_num=5, test_sim='circle_crossing',
+              randomize=True)
+    run_resets()
+    run_rotate()
+
+
+if __name__ == '__main__':
+    main()
