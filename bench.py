@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the batched CrowdSim-v0 step path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--envs 4096] [--humans 5]
+
+Workload (config.workload): BASELINE.json configs[1] = 4096 batched envs x 5 ORCA humans, circle_crossing, ORCA robot,
+robot invisible, per GPU. One bench "step" = one lockstep pass of the hot path over one 4096-env batch: the fused step
+kernel (6 ORCA solves/env, collision/reward/terminal, integration, episode bookkeeping) plus on-device re-generation
+of the scenes of envs whose episode just ended (fresh MT19937 seeds), so every env is live on every step.
+Because 4096 envs of state are only 2.6 MB, the bench rotates through POOLS independent batches whose combined state
+exceeds the 126 MB L2 ("inputs larger than L2"); the batch touched by a step was last touched POOLS steps ago.
+
+Printed JSON keys follow the driver contract; see DESIGN.md "Measurement" for definitions. The oracle (oracle/) is
+executed here ONLY in the cpu_baseline leg and in --impl reference.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'env-steps/sec at 5 humans x batched envs'
+ALG_BYTES = lambda n: 8 * (19 + 12 * n) + 2      # 634 B at N=5, 2074 B at N=20  # noqa: E731
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=600)
+    ap.add_argument('--warmup', type=int, default=100)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--envs', type=int, default=4096, help='envs per batch per GPU')
+    ap.add_argument('--humans', type=int, default=5)
+    ap.add_argument('--pools', type=int, default=0, help='independent batches rotated through (0 = enough to exceed L2)')
+    ap.add_argument('--rule', default='circle_crossing')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.splitlines()[0].split(',')])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = sorted(int(float(r[1])) for r in self.rows if r[1].replace('.', '').isdigit())
+        mx = [int(float(r[2])) for r in self.rows if r[2].replace('.', '').isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[4:8]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(self.rows)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_oracle_rate(args, seconds=12.0, threads=None):
+    """Oracle port (plain C restatement of the reference loop) on the host cores, same workload definition:
+    lockstep passes over a 4096-env batch with auto-reset. Returns (env-steps/s, threads, sample description)."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import pyoracle as po
+    if threads:
+        po.set_threads(threads)
+    nthreads = po.max_threads()
+    B, N = args.envs, args.humans
+    prm = po.default_params()
+    st = po.HostState(B, N); io = po.HostStepIO(B)
+    seeds = (np.arange(B) + 2000).astype(np.uint32)
+    po.reset(st, seeds, args.rule, seed_stride=B)
+    for _ in range(3):
+        po.step(prm, st, io)
+    t0 = time.perf_counter(); n = 0
+    while True:
+        po.step(prm, st, io)
+        po.reset(st, seeds, args.rule, mask=io.done, seed_stride=B)
+        n += 1
+        if n % 8 == 0 and time.perf_counter() - t0 > seconds:
+            break
+    dt = time.perf_counter() - t0
+    return B * n / dt, nthreads, '%d lockstep passes over a %d-env batch (auto-reset), %.1f s' % (n, B, dt)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path = oracle port (the reference is Python + an
+    absent native rvo2; it cannot travel to the GPU box), all host threads, same config/metric."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import pyoracle as po
+    B, N = args.envs, args.humans
+    prm = po.default_params()
+    st = po.HostState(B, N); io = po.HostStepIO(B)
+    seeds = (np.arange(B) + 2000).astype(np.uint32)
+    po.reset(st, seeds, args.rule, seed_stride=B)
+
+    def one():
+        po.step(prm, st, io)
+        po.reset(st, seeds, args.rule, mask=io.done, seed_stride=B)
+    for _ in range(args.warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one()
+    dt = time.perf_counter() - t0
+    v = B * args.steps / dt
+    cores = po.max_threads()
+    line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'env-steps/s', 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64 state + f32 ORCA solver', 'data': 'synthetic',
+            'config': {'workload': '%d batched envs x %d ORCA humans, %s, ORCA robot (invisible), auto-reset' % (B, N, args.rule)},
+            'cpu_baseline': {'value': v, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
+                             'sample': '%d lockstep passes over a %d-env batch per run; C restatement of the reference loop '
+                                       '(oracle/crowdsim_oracle.c, OpenMP over envs)' % (args.steps, B)},
+            'e2e': {'value': v, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from crowdnav_b200 import _abi
+    from crowdnav_b200.batched import BatchedCrowdSim, default_config
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _abi.load()
+    B, N, K, W = args.envs, args.humans, args.steps, args.warmup
+    bytes_per_env = ALG_BYTES(N)
+    pools = args.pools or max(2, int(1.3 * 126e6 / (B * bytes_per_env)) + 1)
+
+    envs = []
+    for p in range(pools):
+        env = BatchedCrowdSim(B, device=dev)
+        env.configure(default_config(human_num=N, test_sim=args.rule, train_val_sim=args.rule))
+        env.set_robot_policy('orca')
+        env.track_episodes(1)
+        env.episodes.ep_case.fill_(-1)
+        # train-phase seeds (crowd_sim.py:272-273): distinct scenes for every env of every pool and rank
+        env.seed_stride = world * pools * B
+        env.reset_seeds(torch.arange(B, dtype=torch.int64) + 2000 + (rank * pools + p) * B, rule=args.rule, seed_stride=env.seed_stride)
+        envs.append(env)
+
+    def step_pool(env):
+        env.step()                                                                        # 1 launch: fused step kernel
+        env.reset_seeds(mask=env.done, rule=args.rule, seed_stride=env.seed_stride)      # 1 launch: scenes of finished envs
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    it = 0
+    for _ in range(max(W, 3)):
+        step_pool(envs[it % pools]); it += 1
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    l0 = lib.crowdsim_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        step_pool(envs[it % pools]); it += 1
+    e1.record()
+    barrier()
+    launches = lib.crowdsim_launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * K / (ms_max * 1e-3)
+
+    # ---- roofline of the dominant kernel: CUDA events around each step-kernel launch, live, same rotating pools ----
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(K, 200))]
+    for a, b in kev:
+        env = envs[it % pools]; it += 1
+        a.record(); env.step(); b.record()
+        env.reset_seeds(mask=env.done, rule=args.rule, seed_stride=env.seed_stride)
+    torch.cuda.synchronize()
+    kms = sorted(a.elapsed_time(b) for a, b in kev)
+    k_avg = sum(kms) / len(kms)
+    peak, peak_src = load_peaks()
+    achieved = B * bytes_per_env / (k_avg * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'kernel': 'cs::step_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': B * bytes_per_env, 'avg_launch_us': 1e3 * k_avg, 'median_launch_us': 1e3 * kms[len(kms) // 2]}
+
+    # ---- e2e: the public API with HOST buffers; H2D of the step's robot actions and D2H of its results, every step ----
+    env = envs[0]
+    env.set_robot_policy('external_xy')
+    h_act = torch.zeros((B, 2), dtype=torch.float64).pin_memory()
+    h_out = {k: torch.empty_like(v, device='cpu').pin_memory() for k, v in
+             (('h_pos', env.state.h_pos), ('h_vel', env.state.h_vel), ('reward', env.reward), ('done', env.done),
+              ('info', env.info), ('next_action', env.action_out))}
+    d_act = torch.zeros((B, 2), dtype=torch.float64, device=dev)
+    d_next = torch.zeros((B, 2), dtype=torch.float64, device=dev)
+    env.orca_act(d_next); h_act.copy_(d_next); torch.cuda.synchronize()
+
+    def e2e_step():
+        d_act.copy_(h_act, non_blocking=True)                      # H2D: this step's robot actions
+        env.step(d_act)
+        env.reset_seeds(mask=env.done, rule=args.rule, seed_stride=env.seed_stride)
+        env.orca_act(d_next)                                       # next decision of the (ORCA) robot policy
+        h_out['h_pos'].copy_(env.state.h_pos, non_blocking=True)   # D2H: observation, reward, done, info, next action
+        h_out['h_vel'].copy_(env.state.h_vel, non_blocking=True)
+        h_out['reward'].copy_(env.reward, non_blocking=True); h_out['done'].copy_(env.done, non_blocking=True)
+        h_out['info'].copy_(env.info, non_blocking=True); h_act.copy_(d_next, non_blocking=True)
+        torch.cuda.current_stream().synchronize()                  # the host reads the results before the next step
+    for _ in range(5):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    ke = min(K, 300)
+    for _ in range(ke):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_dt = time.perf_counter() - t0
+    t = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * ke / float(t.item())
+    h2d = h_act.numel() * 8
+    d2h = sum(v.numel() * v.element_size() for v in h_out.values())
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, sample = cpu_oracle_rate(args)
+        cpu = {'value': v, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
+               'sample': sample + '; C restatement of the reference loop (oracle/crowdsim_oracle.c), OpenMP over envs'}
+
+    if rank == 0:
+        line = {'metric': METRIC, 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': K, 'warmup': max(W, 3),
+                'ms_per_step': ms_max / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'f64 state + f32 ORCA solver', 'data': 'synthetic',
+                'config': {'workload': '%d batched envs x %d ORCA humans, %s, ORCA robot (invisible), auto-reset, per GPU' % (B, N, args.rule),
+                           'envs_per_gpu': B, 'humans': N, 'l2': 'inputs larger than L2: %d rotating independent batches = %.0f MB of state' % (pools, pools * B * bytes_per_env / 1e6),
+                           'parallelism': 'independent envs sharded over %d GPU(s), no data-path collective' % world},
+                'clocks': clocks, 'gpu_launches': int(launches),
+                'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                        'steps': ke, 'note': 'host pinned buffers <-> device every step; robot action uploaded, obs/reward/done/info/next-action downloaded'},
+                'roofline': roofline, 'cpu_baseline': cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -1,0 +1,274 @@
+"""BatchedCrowdSim: B independent CrowdSim-v0 environments stepped in lockstep on one B200.
+
+Host-side driver of libcrowdsim_b200.so (include/crowdsim_b200.h). torch is used only as plumbing: device
+memory (float64 SoA tensors), streams, host<->device copies; every env-step is hand-written CUDA.
+
+Mirrors the reference environment's surface for a batch (paths relative to /root/reference):
+  configure(config)   crowd_sim/envs/crowd_sim.py:51-79   (same RawConfigParser sections/keys)
+  reset(phase, ...)   crowd_sim/envs/crowd_sim.py:251-312 (per-case MT19937 seeding: offset[phase] + case)
+  step(actions)       crowd_sim/envs/crowd_sim.py:317-420 -> (ob, reward, done, info) as tensors
+  onestep_lookahead   crowd_sim/envs/crowd_sim.py:314-315 (batched over the 81-action space, fused with rotate)
+There is no CPU fallback: without the CUDA library / a GPU these calls raise.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _abi
+
+_PHASE_OFFSET = {'train': 2000, 'val': 0, 'test': 1000}   # crowd_sim.py:270-271 (case_capacity val=test=1000)
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def discount_table(gamma, time_step, v_pref, n=128):
+    """explorer.py:71-72: pow(gamma, t * time_step * v_pref) for t = 0..n-1, computed with C pow on the host so the
+    device-side discounted return is bit-identical to the reference's."""
+    return [pow(gamma, t * time_step * v_pref) for t in range(n)]
+
+
+class DeviceState(object):
+    """crowdsim_state on device tensors ([B][N][2] / [B][2] / [B] float64)."""
+    FIELDS = ('h_pos', 'h_vel', 'h_goal', 'h_attr', 'r_pos', 'r_vel', 'r_goal', 'r_attr', 'r_theta', 'g_time')
+
+    def __init__(self, B, N, device):
+        self.B, self.N, self.device = B, N, device
+        z = lambda *s: torch.zeros(s, dtype=torch.float64, device=device)  # noqa: E731
+        self.h_pos, self.h_vel, self.h_goal, self.h_attr = z(B, N, 2), z(B, N, 2), z(B, N, 2), z(B, N, 2)
+        self.r_pos, self.r_vel, self.r_goal, self.r_attr = z(B, 2), z(B, 2), z(B, 2), z(B, 2)
+        self.r_theta, self.g_time = z(B), z(B)
+        self.active = torch.ones(B, dtype=torch.uint8, device=device)
+
+    def struct(self, with_active=True):
+        return _abi.State(*[_ptr(getattr(self, f)) for f in self.FIELDS], _ptr(self.active) if with_active else None)
+
+    def load_host(self, host):
+        """Copy from an object with the same numpy fields (e.g. oracle.pyoracle.HostState in tests)."""
+        for f in self.FIELDS:
+            getattr(self, f).copy_(torch.from_numpy(np.ascontiguousarray(getattr(host, f))))
+        if getattr(host, 'active', None) is not None:
+            self.active.copy_(torch.from_numpy(host.active))
+
+    def to_host(self):
+        out = {f: getattr(self, f).cpu().numpy() for f in self.FIELDS}
+        out['active'] = self.active.cpu().numpy()
+        return out
+
+
+class EpisodeBuffers(object):
+    """crowdsim_episodes: slot accumulators + per-case results of Explorer.run_k_episodes (explorer.py:35-72)."""
+
+    def __init__(self, B, k, device, gamma, time_step, v_pref):
+        i32 = lambda n, v=0: torch.full((n,), v, dtype=torch.int32, device=device)  # noqa: E731
+        f64 = lambda *s: torch.zeros(s, dtype=torch.float64, device=device)  # noqa: E731
+        self.k = k
+        self.ep_case, self.ep_steps, self.ep_too_close = i32(B, -1), i32(B), i32(B)
+        self.ep_return, self.ep_min_dist_sum = f64(B), f64(B)
+        self.discount = torch.tensor(discount_table(gamma, time_step, v_pref), dtype=torch.float64, device=device)
+        self.res_info = torch.zeros(k, dtype=torch.uint8, device=device)
+        self.res_steps, self.res_too_close = i32(k), i32(k)
+        self.res_time, self.res_return, self.res_min_dist_sum = f64(k), f64(k), f64(k)
+        self.res_final_rpos = f64(k, 2)
+
+    def struct(self):
+        return _abi.Episodes(_ptr(self.ep_case), _ptr(self.ep_steps), _ptr(self.ep_return), _ptr(self.ep_too_close),
+                             _ptr(self.ep_min_dist_sum), _ptr(self.discount), self.discount.numel(),
+                             _ptr(self.res_info), _ptr(self.res_steps), _ptr(self.res_time), _ptr(self.res_return),
+                             _ptr(self.res_too_close), _ptr(self.res_min_dist_sum), _ptr(self.res_final_rpos))
+
+
+class BatchedCrowdSim(object):
+    def __init__(self, num_envs, device='cuda:0'):
+        self.lib = _abi.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError('BatchedCrowdSim needs a CUDA device (no CPU fallback)')
+        self.device = torch.device(device)
+        self.B = int(num_envs)
+        # crowd_sim.py:26-49 attributes
+        self.time_limit = None; self.time_step = None
+        self.success_reward = None; self.collision_penalty = None
+        self.discomfort_dist = None; self.discomfort_penalty_factor = None
+        self.config = None; self.case_capacity = None; self.case_size = None; self.case_counter = None
+        self.randomize_attributes = None; self.train_val_sim = None; self.test_sim = None
+        self.square_width = None; self.circle_radius = None; self.human_num = None
+        # robot / humans (agent.py:16-20 config keys)
+        self.robot_visible = False; self.robot_radius = 0.3; self.robot_v_pref = 1.0
+        self.human_radius = 0.3; self.human_v_pref = 1.0
+        self.robot_policy = _abi.ROBOT_ORCA
+        self.human_safety_space = 0.0; self.robot_safety_space = 0.0
+        # ORCA constants (orca.py:61-64)
+        self.neighbor_dist = 10.0; self.max_neighbors = 10; self.time_horizon = 5.0
+        self.state = None; self.episodes = None
+        self._mt_scratch = None
+
+    # ---- configuration -------------------------------------------------------------------------------------------
+    def configure(self, config):
+        """Same keys as crowd_sim.py:51-68 plus the [humans]/[robot] agent attributes of agent.py:16-20."""
+        self.config = config
+        self.time_limit = config.getint('env', 'time_limit')
+        self.time_step = config.getfloat('env', 'time_step')
+        self.randomize_attributes = config.getboolean('env', 'randomize_attributes')
+        self.success_reward = config.getfloat('reward', 'success_reward')
+        self.collision_penalty = config.getfloat('reward', 'collision_penalty')
+        self.discomfort_dist = config.getfloat('reward', 'discomfort_dist')
+        self.discomfort_penalty_factor = config.getfloat('reward', 'discomfort_penalty_factor')
+        if config.get('humans', 'policy') != 'orca':
+            raise NotImplementedError
+        u32max = int(np.iinfo(np.uint32).max)
+        self.case_capacity = {'train': u32max - 2000, 'val': 1000, 'test': 1000}
+        self.case_size = {'train': u32max - 2000, 'val': config.getint('env', 'val_size'),
+                          'test': config.getint('env', 'test_size')}
+        self.train_val_sim = config.get('sim', 'train_val_sim')
+        self.test_sim = config.get('sim', 'test_sim')
+        self.square_width = config.getfloat('sim', 'square_width')
+        self.circle_radius = config.getfloat('sim', 'circle_radius')
+        self.human_num = config.getint('sim', 'human_num')
+        self.case_counter = {'train': 0, 'test': 0, 'val': 0}
+        self.human_radius = config.getfloat('humans', 'radius')
+        self.human_v_pref = config.getfloat('humans', 'v_pref')
+        self.robot_radius = config.getfloat('robot', 'radius')
+        self.robot_v_pref = config.getfloat('robot', 'v_pref')
+        self.robot_visible = config.getboolean('robot', 'visible')
+        self._alloc()
+
+    def _alloc(self):
+        self.state = DeviceState(self.B, self.human_num, self.device)
+        B = self.B
+        self.action = torch.zeros((B, 2), dtype=torch.float64, device=self.device)
+        self.action_out = torch.zeros((B, 2), dtype=torch.float64, device=self.device)
+        self.reward = torch.zeros(B, dtype=torch.float64, device=self.device)
+        self.dmin = torch.zeros(B, dtype=torch.float64, device=self.device)
+        self.done = torch.zeros(B, dtype=torch.uint8, device=self.device)
+        self.info = torch.zeros(B, dtype=torch.uint8, device=self.device)
+        self._seed32 = torch.zeros(B, dtype=torch.int32, device=self.device)
+        self._mt_scratch = torch.empty((624, B), dtype=torch.int32, device=self.device)
+
+    def set_robot_policy(self, kind):
+        self.robot_policy = {'orca': _abi.ROBOT_ORCA, 'external_xy': _abi.ROBOT_EXTERNAL_XY, 'holonomic': _abi.ROBOT_EXTERNAL_XY,
+                             'external_rot': _abi.ROBOT_EXTERNAL_ROT, 'unicycle': _abi.ROBOT_EXTERNAL_ROT}[kind]
+
+    def params(self):
+        return _abi.Params(self.time_step, float(self.time_limit), self.success_reward, self.collision_penalty,
+                           self.discomfort_dist, self.discomfort_penalty_factor, self.neighbor_dist, self.time_horizon,
+                           self.max_neighbors, self.human_safety_space, self.robot_safety_space,
+                           int(bool(self.robot_visible)), self.robot_policy)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- episodes ------------------------------------------------------------------------------------------------
+    def track_episodes(self, k, gamma=0.9):
+        self.episodes = EpisodeBuffers(self.B, k, self.device, gamma, self.time_step, self.robot_v_pref)
+        return self.episodes
+
+    # ---- reset ---------------------------------------------------------------------------------------------------
+    def reset(self, phase='test', cases=None, mask=None, rule=None):
+        """Generate scenes on device. `cases` [B] int (tensor/array) are case numbers of `phase`
+        (seed = offset[phase] + case, crowd_sim.py:270-276); default: consecutive cases from case_counter[phase]."""
+        assert phase in ('train', 'val', 'test')
+        if cases is None:
+            start = self.case_counter[phase]
+            cases = (torch.arange(self.B, dtype=torch.int64) + start) % self.case_size[phase]
+            self.case_counter[phase] = int((start + self.B) % self.case_size[phase])
+        cases = torch.as_tensor(cases, dtype=torch.int64)
+        self.reset_seeds(cases + _PHASE_OFFSET[phase], mask=mask,
+                         rule=rule or (self.test_sim if phase == 'test' else self.train_val_sim))
+        return self.observation()
+
+    def set_seeds(self, seeds):
+        """Load per-slot MT19937 seeds (any integer tensor/array, values in [0, 2**32))."""
+        seeds = torch.as_tensor(seeds, dtype=torch.int64).to(self.device, non_blocking=True)
+        # uint32 bit patterns stored in an int32 tensor
+        self._seed32.copy_(((seeds + 2 ** 31) % 2 ** 32 - 2 ** 31).to(torch.int32))
+
+    def reset_seeds(self, seeds=None, mask=None, rule='circle_crossing', seed_stride=0):
+        """crowdsim_reset for the envs selected by `mask` (uint8 device tensor, None = all) from the per-slot seeds.
+        With seed_stride != 0 the slot's seed is advanced on device after use (auto-reset without host work)."""
+        if seeds is not None:
+            self.set_seeds(seeds)
+        if mask is not None and not (isinstance(mask, torch.Tensor) and mask.dtype == torch.uint8 and mask.device == self.device):
+            mask = torch.as_tensor(mask).to(device=self.device, dtype=torch.uint8)
+        a = _abi.ResetArgs(_ptr(mask), _ptr(self._seed32), int(seed_stride) % 2 ** 32, _abi.RULES[rule], self.circle_radius,
+                           self.square_width, self.human_radius, self.human_v_pref, self.robot_radius, self.robot_v_pref,
+                           self.discomfort_dist, int(bool(self.randomize_attributes)), _ptr(self._mt_scratch))
+        st = self.state.struct()
+        ep = self.episodes.struct() if self.episodes is not None else None
+        rc = self.lib.crowdsim_reset(C.byref(a), self.B, self.human_num, C.byref(st),
+                                     C.byref(ep) if ep is not None else None, self._stream())
+        _abi.check(rc, 'crowdsim_reset')
+        self._keep = (mask, a)
+
+    # ---- step ----------------------------------------------------------------------------------------------------
+    def step(self, actions=None):
+        """One lockstep env-step. `actions` [B][2] float64 device tensor (vx,vy) / (v,r); None when the robot runs ORCA."""
+        if self.robot_policy != _abi.ROBOT_ORCA:
+            if actions is None:
+                raise ValueError('robot policy is external: actions required')
+            if actions.data_ptr() != self.action.data_ptr():
+                self.action.copy_(actions, non_blocking=True)
+        prm = self.params()
+        st = self.state.struct()
+        io = _abi.StepIO(_ptr(self.action), _ptr(self.action_out), _ptr(self.reward), _ptr(self.dmin),
+                         _ptr(self.done), _ptr(self.info))
+        ep = self.episodes.struct() if self.episodes is not None else None
+        rc = self.lib.crowdsim_step(C.byref(prm), self.B, self.human_num, C.byref(st), C.byref(io),
+                                    C.byref(ep) if ep is not None else None, self._stream())
+        _abi.check(rc, 'crowdsim_step')
+        return self.observation(), self.reward, self.done, self.info
+
+    def orca_act(self, out=None):
+        out = self.action_out if out is None else out
+        prm = self.params(); st = self.state.struct()
+        rc = self.lib.crowdsim_orca_act(C.byref(prm), self.B, self.human_num, C.byref(st), _ptr(out), self._stream())
+        _abi.check(rc, 'crowdsim_orca_act')
+        return out
+
+    def observation(self):
+        """[B][N][5] view material: (px, py, vx, vy, radius) of each human (agent.py:60-61), as separate tensors."""
+        s = self.state
+        return s.h_pos, s.h_vel, s.h_attr[..., 0]
+
+    # ---- value-network support -----------------------------------------------------------------------------------
+    def pack_joint(self, unicycle=False, out=None):
+        if out is None:
+            out = torch.empty((self.B, self.human_num, 13), dtype=torch.float32, device=self.device)
+        st = self.state.struct()
+        rc = self.lib.crowdsim_pack_joint(self.B, self.human_num, C.byref(st), int(unicycle), _ptr(out), self._stream())
+        _abi.check(rc, 'crowdsim_pack_joint')
+        return out
+
+    def lookahead_pack(self, actions, unicycle=False, out_states=None, out_reward=None):
+        """actions [A][2] float64 device tensor -> (states [B][A][N][13] f32, reward [B][A] f64)."""
+        A = actions.shape[0]
+        if out_states is None:
+            out_states = torch.empty((self.B, A, self.human_num, 13), dtype=torch.float32, device=self.device)
+        if out_reward is None:
+            out_reward = torch.empty((self.B, A), dtype=torch.float64, device=self.device)
+        prm = self.params(); st = self.state.struct()
+        rc = self.lib.crowdsim_lookahead_pack(C.byref(prm), self.B, self.human_num, C.byref(st), _ptr(actions), A,
+                                              int(unicycle), _ptr(out_states), _ptr(out_reward), self._stream())
+        _abi.check(rc, 'crowdsim_lookahead_pack')
+        return out_states, out_reward
+
+
+def default_config(human_num=5, test_sim='circle_crossing', train_val_sim='circle_crossing', robot_visible=False,
+                   randomize_attributes=False):
+    """The reference's crowd_nav/configs/env.config:1-37 as a RawConfigParser (values restated, not read from disk)."""
+    import configparser
+    cfg = configparser.RawConfigParser()
+    cfg.read_dict({
+        'env': {'time_limit': '25', 'time_step': '0.25', 'val_size': '100', 'test_size': '500',
+                'randomize_attributes': 'true' if randomize_attributes else 'false'},
+        'reward': {'success_reward': '1', 'collision_penalty': '-0.25', 'discomfort_dist': '0.2',
+                   'discomfort_penalty_factor': '0.5'},
+        'sim': {'train_val_sim': train_val_sim, 'test_sim': test_sim, 'square_width': '10', 'circle_radius': '4',
+                'human_num': str(human_num)},
+        'humans': {'visible': 'true', 'policy': 'orca', 'radius': '0.3', 'v_pref': '1', 'sensor': 'coordinates'},
+        'robot': {'visible': 'true' if robot_visible else 'false', 'policy': 'none', 'radius': '0.3', 'v_pref': '1',
+                  'sensor': 'coordinates'},
+    })
+    return cfg

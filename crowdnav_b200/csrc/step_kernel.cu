@@ -1,0 +1,219 @@
+// step_kernel.cu -- one lockstep CrowdSim-v0 env-step for B environments (sm_100a).
+//
+// Replaces, for every env of the batch, crowd_sim/envs/crowd_sim.py:317-420 (CrowdSim.step, update=True):
+//   N x Human.act -> ORCA.predict (orca.py:82-132, float32 RVO2 arithmetic, see orca_device.cuh),
+//   optionally the robot's own ORCA.predict (explorer.py:42 with --policy orca),
+//   robot-human swept-segment collision / min clearance (crowd_sim.py:331-351, utils.py:4-26), float64,
+//   goal / timeout / reward ladder (crowd_sim.py:365-389), Euler integration (agent.py:122-135),
+//   and Explorer.run_k_episodes' per-step bookkeeping (explorer.py:41-72).
+//
+// Mapping: one thread per (env, agent) -- L = N + 1 lanes per env (humans 0..N-1, lane N = robot), EPB envs per
+// block, dense (an env's lanes may straddle a warp; all intra-env exchange goes through shared memory). Each lane
+// loads its own agent with 16-byte loads (consecutive lanes -> consecutive addresses in the [B][N][2] arrays),
+// stages it in shared memory for the other lanes' neighbour scans, solves its own ORCA problem, and writes its own
+// agent back. HBM traffic per env-step is exactly the algorithmic 8*(19+12N)+2 bytes (+ episode bookkeeping).
+#include "crowdsim_common.cuh"
+
+namespace cs {
+
+unsigned long long g_launches = 0;
+
+struct StepArgs {
+    KParams k;
+    int B, N, L, EPB;
+    crowdsim_state st;
+    crowdsim_step_io io;
+    crowdsim_episodes ep;
+    int has_ep;
+    int act_only;      // crowdsim_orca_act: robot lanes solve and write action_out, nothing is mutated
+};
+
+__global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int T = blockDim.x, tid = threadIdx.x;
+    const int N = A.N, L = A.L;
+    const KParams &k = A.k;
+    const Stage s = carve_stage(smem, A.EPB, L, k.nb_alloc, T);
+
+    const int le = tid / L, a = tid - le * L;
+    const int e = blockIdx.x * A.EPB + le;
+    const bool is_robot = (a == N);
+    bool live = (e < A.B);
+    if (live && A.st.active) live = (A.st.active[e] != 0);
+
+    // ---- load own agent (coalesced 16-byte loads) and stage it ----
+    double2 pos = make_double2(0, 0), vel = pos, goal = pos, attr = pos;
+    double theta = 0, gtime = 0;
+    if (live) {
+        if (!is_robot) {
+            const size_t i = (size_t)e * N + a;
+            pos = ld2(A.st.h_pos, i); vel = ld2(A.st.h_vel, i); goal = ld2(A.st.h_goal, i); attr = ld2(A.st.h_attr, i);
+        } else {
+            pos = ld2(A.st.r_pos, e); vel = ld2(A.st.r_vel, e); goal = ld2(A.st.r_goal, e); attr = ld2(A.st.r_attr, e);
+            gtime = A.st.g_time[e];
+            if (k.robot_policy == CROWDSIM_ROBOT_EXTERNAL_ROT) theta = A.st.r_theta[e];
+        }
+    }
+    stage_agent(s, k, tid, pos, vel, attr.x);
+    __syncthreads();
+
+    // ---- ORCA solves: every human lane; the robot lane iff the robot runs ORCA ----
+    orca::V2 nv = orca::mk(0.f, 0.f);
+    const bool solve = live && (!is_robot || k.robot_policy == CROWDSIM_ROBOT_ORCA) && !(A.act_only && !is_robot);
+    if (solve) nv = orca_predict(s, k, le, a, N, L, pos, goal, attr.y, tid, T);
+
+    if (A.act_only) {
+        if (live && is_robot) st2(A.io.action_out, e, make_double2((double)nv.x, (double)nv.y));
+        return;
+    }
+
+    // ---- robot lane publishes the velocity it applies this step ----
+    double ax = 0, ay = 0;            // raw action: (vx, vy) or (v, r)
+    double2 rvel = make_double2(0, 0); // world-frame velocity used by the collision test
+    if (live && is_robot) {
+        if (k.robot_policy == CROWDSIM_ROBOT_ORCA) { ax = (double)nv.x; ay = (double)nv.y; rvel = make_double2(ax, ay); }
+        else {
+            const double2 act = ld2(A.io.action, e); ax = act.x; ay = act.y;
+            if (k.robot_policy == CROWDSIM_ROBOT_EXTERNAL_ROT) rvel = make_double2(ax * cos(ay + theta), ax * sin(ay + theta));  // crowd_sim.py:340-341
+            else rvel = act;
+        }
+        s.act[le] = rvel;
+    }
+    __syncthreads();
+
+    // ---- human lanes: swept-segment clearance against the robot (crowd_sim.py:333-345) ----
+    const double dt = k.time_step;
+    if (live && !is_robot) {
+        const double2 rp = s.pos64[le * L + N], ra = s.act[le];
+        const double px = pos.x - rp.x, py = pos.y - rp.y;
+        const double vx = vel.x - ra.x, vy = vel.y - ra.y;     // human's CURRENT velocity attribute (previous action)
+        const double ex = px + vx * dt, ey = py + vy * dt;
+        s.closest[tid] = point_to_segment_dist0(px, py, ex, ey) - attr.x - s.rad64[le * L + N];
+    }
+    __syncthreads();
+
+    if (!live) return;
+    if (!is_robot) {
+        // agent.py:122-135 holonomic step with the ORCA action (float32 values widened)
+        const double hx = (double)nv.x, hy = (double)nv.y;
+        const size_t i = (size_t)e * N + a;
+        st2(A.st.h_pos, i, make_double2(pos.x + hx * dt, pos.y + hy * dt));
+        st2(A.st.h_vel, i, make_double2(hx, hy));
+        return;
+    }
+
+    // ---- robot lane: reduce clearances, ladder, update, bookkeeping ----
+    double dmin = __longlong_as_double(0x7ff0000000000000LL); bool collision = false;
+    for (int i = 0; i < N; ++i) {           // crowd_sim.py:346-351 (first collision breaks; dmin only matters without one)
+        const double c = s.closest[le * L + i];
+        if (c < 0) { collision = true; break; }
+        else if (c < dmin) dmin = c;
+    }
+    double npx, npy, nvx, nvy;
+    if (k.robot_policy != CROWDSIM_ROBOT_EXTERNAL_ROT) { npx = pos.x + ax * dt; npy = pos.y + ay * dt; nvx = ax; nvy = ay; }
+    else { const double th = theta + ay; npx = pos.x + cos(th) * ax * dt; npy = pos.y + sin(th) * ax * dt; nvx = nvy = 0; }  // agent.py:115-118
+    const bool reaching_goal = norm2(npx - goal.x, npy - goal.y) < attr.x;      // crowd_sim.py:365-366
+
+    double reward; bool done; int info;                                        // crowd_sim.py:368-389
+    if (gtime >= k.time_limit - 1) { reward = 0; done = true; info = CROWDSIM_INFO_TIMEOUT; }
+    else if (collision) { reward = k.collision_penalty; done = true; info = CROWDSIM_INFO_COLLISION; }
+    else if (reaching_goal) { reward = k.success_reward; done = true; info = CROWDSIM_INFO_REACHGOAL; }
+    else if (dmin < k.discomfort_dist) { reward = (dmin - k.discomfort_dist) * k.discomfort_penalty_factor * dt; done = false; info = CROWDSIM_INFO_DANGER; }
+    else { reward = 0; done = false; info = CROWDSIM_INFO_NOTHING; }
+
+    if (k.robot_policy == CROWDSIM_ROBOT_EXTERNAL_ROT) {                        // agent.py:133-135
+        double nth = fmod(theta + ay, 2 * CS_PI); if (nth < 0) nth += 2 * CS_PI;
+        A.st.r_theta[e] = nth; nvx = ax * cos(nth); nvy = ax * sin(nth);
+    }
+    st2(A.st.r_pos, e, make_double2(npx, npy));
+    st2(A.st.r_vel, e, make_double2(nvx, nvy));
+    const double ntime = gtime + dt;
+    A.st.g_time[e] = ntime;
+    if (A.io.action_out) st2(A.io.action_out, e, make_double2(nvx, nvy));
+    A.io.reward[e] = reward; A.io.dmin[e] = dmin; A.io.done[e] = done ? 1 : 0; A.io.info[e] = (uint8_t)info;
+
+    if (A.has_ep) {                                                            // explorer.py:41-72
+        const crowdsim_episodes &ep = A.ep;
+        const int t = ep.ep_steps[e];
+        const double disc = (t < ep.discount_len) ? ep.discount[t] : 0.0;
+        const double ret = ep.ep_return[e] + disc * reward;
+        int tc = ep.ep_too_close[e]; double mds = ep.ep_min_dist_sum[e];
+        if (info == CROWDSIM_INFO_DANGER) { tc += 1; mds += dmin; ep.ep_too_close[e] = tc; ep.ep_min_dist_sum[e] = mds; }
+        ep.ep_return[e] = ret; ep.ep_steps[e] = t + 1;
+        if (done) {
+            const int c = ep.ep_case[e];
+            if (c >= 0) {
+                ep.res_info[c] = (uint8_t)info; ep.res_steps[c] = t + 1;
+                ep.res_time[c] = (info == CROWDSIM_INFO_TIMEOUT) ? k.time_limit : ntime;
+                ep.res_return[c] = ret; ep.res_too_close[c] = tc; ep.res_min_dist_sum[c] = mds;
+                if (ep.res_final_rpos) st2(ep.res_final_rpos, c, make_double2(npx, npy));
+            }
+            if (A.st.active) A.st.active[e] = 0;
+        }
+    }
+}
+
+static int launch(const crowdsim_params *prm, int B, int N, const crowdsim_state *st, const crowdsim_step_io *io,
+                  const crowdsim_episodes *ep, int act_only, cudaStream_t stream)
+{
+    if (!prm || !st || !io || B < 0 || N < 0) return CROWDSIM_EINVAL;
+    if (N > CROWDSIM_MAX_HUMANS || prm->max_neighbors > CROWDSIM_MAX_NEIGHBORS) return CROWDSIM_EUNSUPPORTED;
+    if (N > 0 && (!st->h_pos || !st->h_vel || !st->h_goal || !st->h_attr)) return CROWDSIM_EINVAL;
+    if (!st->r_pos || !st->r_vel || !st->r_goal || !st->r_attr || !st->g_time) return CROWDSIM_EINVAL;
+    if (prm->robot_policy == CROWDSIM_ROBOT_EXTERNAL_ROT && !st->r_theta) return CROWDSIM_EINVAL;
+    if (act_only) { if (!io->action_out) return CROWDSIM_EINVAL; }
+    else {
+        if (!io->reward || !io->dmin || !io->done || !io->info) return CROWDSIM_EINVAL;
+        if (prm->robot_policy != CROWDSIM_ROBOT_ORCA && !io->action) return CROWDSIM_EINVAL;
+    }
+    if (ep && !act_only && (!ep->ep_case || !ep->ep_steps || !ep->ep_return || !ep->ep_too_close || !ep->ep_min_dist_sum ||
+                            !ep->discount || !ep->res_info || !ep->res_steps || !ep->res_time || !ep->res_return ||
+                            !ep->res_too_close || !ep->res_min_dist_sum)) return CROWDSIM_EINVAL;
+    if (B == 0) return CROWDSIM_OK;
+    StepArgs A;
+    A.k = make_kparams(prm, N);
+    if (act_only) A.k.robot_policy = CROWDSIM_ROBOT_ORCA;
+    A.B = B; A.N = N; A.L = N + 1; A.EPB = envs_per_block(A.L, 128);
+    A.st = *st; A.io = *io; A.has_ep = (ep != nullptr && !act_only); A.act_only = act_only;
+    if (A.has_ep) A.ep = *ep; else memset(&A.ep, 0, sizeof(A.ep));
+    const int threads = A.EPB * A.L;
+    const int blocks = (B + A.EPB - 1) / A.EPB;
+    const size_t smem = stage_bytes(A.EPB, A.L, A.k.nb_alloc, threads);
+    if (smem > 48 * 1024) {
+        cudaError_t err = cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return (int)err;
+    }
+    step_kernel<<<blocks, threads, smem, stream>>>(A);
+    ++g_launches;
+    return (int)cudaGetLastError();
+}
+
+}  // namespace cs
+
+extern "C" int crowdsim_step(const crowdsim_params *prm, int B, int N, crowdsim_state *st, crowdsim_step_io *io,
+                             crowdsim_episodes *ep, void *stream)
+{
+    return cs::launch(prm, B, N, st, io, ep, 0, (cudaStream_t)stream);
+}
+
+extern "C" int crowdsim_orca_act(const crowdsim_params *prm, int B, int N, const crowdsim_state *st, double *action_out,
+                                 void *stream)
+{
+    crowdsim_step_io io; memset(&io, 0, sizeof(io)); io.action_out = action_out;
+    return cs::launch(prm, B, N, st, &io, nullptr, 1, (cudaStream_t)stream);
+}
+
+extern "C" int crowdsim_abi_version(void) { return CROWDSIM_ABI_VERSION; }
+
+extern "C" unsigned long long crowdsim_launch_count(void) { return cs::g_launches; }
+
+extern "C" int crowdsim_device_check(int *sm_count, int *cc_major, int *cc_minor)
+{
+    int dev = 0; cudaDeviceProp p;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&p, dev) != cudaSuccess) return CROWDSIM_ENODEVICE;
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    return (p.major == 10) ? CROWDSIM_OK : CROWDSIM_ENODEVICE;
+}

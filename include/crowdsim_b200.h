@@ -130,7 +130,9 @@ typedef struct crowdsim_episodes {
 /* Scenario generation request for crowdsim_reset. */
 typedef struct crowdsim_reset_args {
     const uint8_t *mask;     /* [B] or NULL: reset only envs with mask[e] != 0 (NULL = all) */
-    const uint32_t *seed;    /* [B] MT19937 seed per env (crowd_sim.py:272-276: offset[phase] + case) */
+    uint32_t *seed;          /* [B] MT19937 seed per env (crowd_sim.py:272-276: offset[phase] + case); after a masked env
+                                has been reset its entry is advanced by seed_stride (next scene of that slot) */
+    uint32_t seed_stride;    /* 0 = leave seeds untouched */
     int32_t rule;            /* CROWDSIM_RULE_* */
     double circle_radius;    /* env.config [sim] circle_radius = 4 */
     double square_width;     /* env.config [sim] square_width  = 10 */

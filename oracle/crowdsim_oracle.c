@@ -22,6 +22,25 @@
 #include <string.h>
 #include "../include/crowdsim_b200.h"
 #include "rvo2_f32.h"
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* thread control for bench.py (cpu_baseline / --impl reference) */
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+int oracle_get_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
 
 #define PI_D 3.141592653589793   /* numpy.pi */
 
@@ -69,6 +88,7 @@ void oracle_mt19937_doubles(uint32_t seed, int n, double *out)
 static void reset_one(const crowdsim_reset_args *a, int e, int N, crowdsim_state *st)
 {
     mt_state rng; mt_seed(&rng, a->seed[e]);
+    if (a->seed_stride) a->seed[e] += a->seed_stride;
     double *hp = st->h_pos + (size_t)e * N * 2, *hv = st->h_vel + (size_t)e * N * 2;
     double *hg = st->h_goal + (size_t)e * N * 2, *ha = st->h_attr + (size_t)e * N * 2;
     /* crowd_sim.py:274 robot.set(0, -R, 0, R, 0, 0, pi/2) */

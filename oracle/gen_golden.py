@@ -89,7 +89,10 @@ def scene(env):
     }
 
 
-def run_suite(name, cases, phase='test', gamma=0.9, record_traj=(), **kw):
+def run_suite(name, cases, phase='test', gamma=0.9, record_traj=(), fresh_robot_sim=False, **kw):
+    """fresh_robot_sim: drop the robot's cached rvo2 sim before every episode. The reference keeps it across
+    episodes (orca.py:95-104), so with randomize_attributes the robot would keep solving with the human radii of
+    the FIRST episode it saw -- an accident of object lifetime we do not reproduce."""
     env, robot, _ = make_env(**kw)
     # 1) the reference's own Explorer, capturing its log lines
     stream = io.StringIO()
@@ -110,6 +113,8 @@ def run_suite(name, cases, phase='test', gamma=0.9, record_traj=(), **kw):
     trajs = {}
     total_steps = 0
     for case in cases:
+        if fresh_robot_sim:
+            robot.policy.sim = None
         ob = env.reset(phase, case)
         init = scene(env)
         done = False
@@ -139,6 +144,8 @@ def run_suite(name, cases, phase='test', gamma=0.9, record_traj=(), **kw):
             trajs[str(case)] = steps
     counts = {k: sum(1 for c in per_case if c['info'] == v) for k, v in
               (('success', 2), ('collision', 3), ('timeout', 4))}
+    if fresh_robot_sim:
+        log_lines = []      # Explorer ran with the stale-radius sim; its aggregate lines do not apply
     out = {'name': name, 'phase': phase, 'config': {k: (v if not isinstance(v, bool) else v) for k, v in kw.items()},
            'gamma': gamma, 'log_lines': log_lines, 'counts': counts, 'total_env_steps': total_steps,
            'cases': per_case}
@@ -232,7 +239,7 @@ def main():
     run_suite('circle10_visible', list(range(20 if quick else 100)), human_num=10, test_sim='circle_crossing',
               robot_visible=True)
     run_suite('circle5_random_attr', list(range(20 if quick else 100)), human_num=5, test_sim='circle_crossing',
-              randomize=True)
+              randomize=True, fresh_robot_sim=True)
     run_resets()
     run_rotate()
 

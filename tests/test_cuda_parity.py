@@ -1,0 +1,267 @@
+"""GPU parity tests: the CUDA library (through its C ABI, crowdnav_b200/_abi.py) against the CPU oracle and the
+committed golden fixtures of the reference. Bar: bit-exact for flags / integer fields AND (in practice) for every
+float64 state array, because both sides evaluate the same individually-rounded operations; the only tolerated
+differences are CUDA's double cos/sin in scenario generation (<= 4 ulp on initial coordinates) and the float32
+atan2f/cosf/sinf of the rotate rows (1e-5)."""
+import numpy as np
+import pytest
+import torch
+
+from util import SUITES, load_golden, scene_arrays, fill_host_state, ulp_diff
+
+pytestmark = pytest.mark.gpu
+
+STATE_FIELDS = ('h_pos', 'h_vel', 'h_goal', 'h_attr', 'r_pos', 'r_vel', 'r_goal', 'r_attr', 'g_time')
+
+
+def _assert_state_equal(env, host, fields=STATE_FIELDS, what=''):
+    dev = env.state.to_host()
+    for f in fields:
+        a, b = dev[f], getattr(host, f)
+        assert np.array_equal(a, b), '%s: field %s differs in %d entries (max abs %.3g)' % (
+            what, f, int((a != b).sum()), float(np.abs(a - b).max()))
+
+
+def _assert_io_equal(env, io, what=''):
+    assert np.array_equal(env.done.cpu().numpy(), io.done), what + ' done'
+    assert np.array_equal(env.info.cpu().numpy(), io.info), what + ' info'
+    assert np.array_equal(env.reward.cpu().numpy(), io.reward), what + ' reward'
+    assert np.array_equal(env.dmin.cpu().numpy(), io.dmin), what + ' dmin'
+    assert np.array_equal(env.action_out.cpu().numpy(), io.action_out), what + ' action_out'
+
+
+def _random_host_state(oracle, B, N, seed, spread=4.5):
+    rng = np.random.RandomState(seed)
+    st = oracle.HostState(B, N)
+    st.h_pos[...] = rng.uniform(-spread, spread, (B, N, 2))
+    st.h_vel[...] = rng.uniform(-1, 1, (B, N, 2)).astype(np.float32)          # velocities are float32-valued actions
+    st.h_goal[...] = rng.uniform(-spread, spread, (B, N, 2))
+    st.h_attr[..., 0] = rng.uniform(0.2, 0.5, (B, N)); st.h_attr[..., 1] = rng.uniform(0.5, 1.5, (B, N))
+    st.r_pos[...] = rng.uniform(-spread, spread, (B, 2)); st.r_vel[...] = rng.uniform(-1, 1, (B, 2)).astype(np.float32)
+    st.r_goal[...] = rng.uniform(-spread, spread, (B, 2))
+    st.r_attr[:, 0] = rng.uniform(0.2, 0.5, B); st.r_attr[:, 1] = rng.uniform(0.5, 1.5, B)
+    st.r_theta[...] = rng.uniform(0, 2 * np.pi, B)
+    st.g_time[...] = 0.25 * rng.randint(0, 99, B)
+    return st
+
+
+@pytest.mark.parametrize('name', ['circle5_invisible', 'square5_invisible', 'square20_invisible', 'circle5_visible'])
+def test_step_reproduces_golden_trajectories(cuda_env, oracle, name):
+    """Each recorded reference step (pre-state, action, reward, info, post-state) is reproduced bit-exactly."""
+    N, rule, vis, _ = SUITES[name]
+    d = load_golden('traj_' + name)
+    for case, steps in d['trajectories'].items():
+        host = fill_host_state(oracle, [s['pre'] for s in steps], N)
+        host.g_time[:] = [float(s['global_time']) - 0.25 for s in steps]
+        env = cuda_env(len(steps), N, rule, robot_visible=bool(vis))
+        env.state.load_host(host)
+        env.step()
+        torch.cuda.synchronize()
+        dev = env.state.to_host()
+        for e, s in enumerate(steps):
+            r, h = scene_arrays(s['post'])
+            assert (env.action_out[e].cpu().numpy() == [float(x) for x in s['action']]).all(), (name, case, e)
+            assert float(env.reward[e]) == float(s['reward']) and int(env.done[e]) == int(s['done']) and int(env.info[e]) == s['info']
+            if s['dmin'] is not None:
+                assert float(env.dmin[e]) == float(s['dmin'])
+            assert (dev['r_pos'][e] == r[0:2]).all() and (dev['h_pos'][e] == h[:, 0:2]).all() and (dev['h_vel'][e] == h[:, 2:4]).all()
+
+
+@pytest.mark.parametrize('N,vis,policy', [(5, 0, 'orca'), (5, 1, 'orca'), (1, 0, 'orca'), (2, 1, 'external_xy'),
+                                          (10, 1, 'orca'), (11, 0, 'orca'), (20, 0, 'orca'), (20, 1, 'external_xy'),
+                                          (33, 1, 'orca'), (63, 1, 'orca'), (0, 0, 'orca'), (5, 0, 'external_rot')])
+def test_step_random_scenes_bit_exact(cuda_env, oracle, N, vis, policy):
+    """Dense random scenes (many overlapping agents -> collision branch, lp3 fallback, 10-of-N truncation),
+    8 consecutive steps, every state/output array compared for equality with the CPU oracle."""
+    B = 1500 if N <= 20 else 300
+    host = _random_host_state(oracle, B, N, seed=100 + N)
+    env = cuda_env(B, N, robot_visible=bool(vis), robot_policy=policy)
+    env.state.load_host(host)
+    from crowdnav_b200 import _abi
+    prm = oracle.default_params(robot_visible=vis, robot_policy={'orca': _abi.ROBOT_ORCA, 'external_xy': _abi.ROBOT_EXTERNAL_XY,
+                                                                 'external_rot': _abi.ROBOT_EXTERNAL_ROT}[policy])
+    io = oracle.HostStepIO(B)
+    rng = np.random.RandomState(5)
+    for t in range(8):
+        if policy == 'external_rot':
+            io.action[:, 0] = rng.uniform(0, 1, B); io.action[:, 1] = rng.uniform(-0.8, 0.8, B)
+        else:
+            io.action[...] = rng.uniform(-1, 1, (B, 2))
+        act = torch.from_numpy(io.action).to(env.device)
+        env.step(None if policy == 'orca' else act)
+        oracle.step(prm, host, io)
+        torch.cuda.synchronize()
+        if policy == 'external_rot':
+            # CUDA's double cos/sin are not glibc's: compare with a tolerance, then resynchronise the states
+            dev = env.state.to_host()
+            for f in ('h_pos', 'h_vel'):
+                assert np.array_equal(dev[f], getattr(host, f))
+            assert np.allclose(dev['r_pos'], host.r_pos, rtol=0, atol=1e-12) and np.allclose(dev['r_theta'], host.r_theta, rtol=0, atol=1e-12)
+            assert np.array_equal(env.info.cpu().numpy(), io.info)
+            env.state.load_host(host)
+        else:
+            _assert_state_equal(env, host, what='N=%d step %d' % (N, t))
+            _assert_io_equal(env, io, what='N=%d step %d' % (N, t))
+
+
+@pytest.mark.parametrize('name', sorted(SUITES))
+def test_full_suites_from_reference_scenes(cuda_env, oracle, name):
+    """Whole episodes on the GPU from the reference's own initial scenes: terminal class, step count, time, discounted
+    return, danger statistics and final positions identical to the reference's Python for every test case."""
+    N, rule, vis, rand = SUITES[name]
+    cases = load_golden('suite_' + name)['cases']
+    B = len(cases)
+    host = fill_host_state(oracle, [c['init'] for c in cases], N)
+    env = cuda_env(B, N, rule, robot_visible=bool(vis))
+    ep = env.track_episodes(B)
+    env.state.load_host(host)
+    ep.ep_case.copy_(torch.arange(B, dtype=torch.int32))
+    for _ in range(110):
+        env.step()
+    torch.cuda.synchronize()
+    assert int(env.state.active.sum()) == 0
+    info = ep.res_info.cpu().numpy(); steps = ep.res_steps.cpu().numpy(); t = ep.res_time.cpu().numpy()
+    ret = ep.res_return.cpu().numpy(); tc = ep.res_too_close.cpu().numpy(); mds = ep.res_min_dist_sum.cpu().numpy()
+    frp = ep.res_final_rpos.cpu().numpy(); hp = env.state.h_pos.cpu().numpy()
+    for i, c in enumerate(cases):
+        assert info[i] == c['info'] and steps[i] == c['steps'], (name, c['case'])
+        assert t[i] == (25.0 if c['info'] == 4 else float(c['global_time']))
+        assert ret[i] == float(c['return']) and tc[i] == c['too_close'] and mds[i] == float(c['min_dist_sum'])
+        r, h = scene_arrays(c['final'])
+        assert (frp[i] == r[:2]).all() and (hp[i] == h[:, :2]).all()
+
+
+@pytest.mark.parametrize('name', ['circle5_invisible', 'square5_invisible', 'square20_invisible', 'circle5_visible'])
+def test_full_suites_device_reset(cuda_env, name):
+    """Same, but with scenes generated ON DEVICE from the case seeds (crowdsim_reset). Flags bit-exact, positions
+    within 1e-5 (north_star bar; CUDA cos/sin may move initial coordinates by an ulp)."""
+    N, rule, vis, _ = SUITES[name]
+    cases = load_golden('suite_' + name)['cases']
+    B = len(cases)
+    env = cuda_env(B, N, rule, robot_visible=bool(vis))
+    ep = env.track_episodes(B)
+    env.reset('test', cases=[c['case'] for c in cases])
+    ep.ep_case.copy_(torch.arange(B, dtype=torch.int32))
+    for _ in range(110):
+        env.step()
+    torch.cuda.synchronize()
+    info = ep.res_info.cpu().numpy(); steps = ep.res_steps.cpu().numpy(); frp = ep.res_final_rpos.cpu().numpy()
+    assert [int(x) for x in info] == [c['info'] for c in cases]
+    assert [int(x) for x in steps] == [c['steps'] for c in cases]
+    fr = np.array([scene_arrays(c['final'])[0][:2] for c in cases])
+    assert np.abs(frp - fr).max() < 1e-5
+
+
+def test_reset_matches_oracle(cuda_env, oracle):
+    worst = 0
+    for N, rule, rand in [(5, 'circle_crossing', False), (5, 'square_crossing', False), (20, 'square_crossing', False),
+                          (10, 'circle_crossing', True), (5, 'square_crossing', True)]:
+        B = 2000
+        seeds = np.concatenate([np.arange(1000, 1500), np.arange(2000, 3000), [0, 1, 99, 4294967295, 4294965295],
+                                np.random.RandomState(1).randint(0, 2 ** 32, B - 1505, dtype=np.uint64)]).astype(np.uint64)
+        host = oracle.HostState(B, N)
+        oracle.reset(host, seeds.astype(np.uint32), rule, randomize_attributes=rand)
+        env = cuda_env(B, N, rule, randomize=rand)
+        env.reset_seeds(torch.from_numpy(seeds.astype(np.int64)), rule=rule)
+        torch.cuda.synchronize()
+        dev = env.state.to_host()
+        for f in ('h_attr', 'r_pos', 'r_goal', 'r_attr', 'r_vel', 'h_vel', 'g_time', 'r_theta'):
+            assert np.array_equal(dev[f], getattr(host, f)), f
+        for f in ('h_pos', 'h_goal'):
+            d = ulp_diff(dev[f], getattr(host, f)).max()
+            worst = max(worst, int(d))
+            assert d <= 4, (N, rule, f, d)
+        if rule == 'square_crossing':        # no cos/sin on this path: bit-exact
+            assert np.array_equal(dev['h_pos'], host.h_pos) and np.array_equal(dev['h_goal'], host.h_goal)
+    print('worst ulp distance of initial coordinates:', worst)
+
+
+def test_reset_mask_and_active(cuda_env, oracle):
+    B, N = 300, 5
+    env = cuda_env(B, N)
+    env.reset_seeds(torch.arange(B) + 2000)
+    before = env.state.to_host()
+    mask = (np.arange(B) % 3 == 0).astype(np.uint8)
+    env.state.active.zero_()
+    env.reset_seeds(torch.arange(B) + 5000, mask=torch.from_numpy(mask))
+    after = env.state.to_host()
+    assert np.array_equal(after['h_pos'][mask == 0], before['h_pos'][mask == 0])
+    assert not np.array_equal(after['h_pos'][mask == 1], before['h_pos'][mask == 1])
+    assert np.array_equal(after['active'], mask)
+    # frozen envs are not touched by a step
+    snap = env.state.to_host()
+    env.step()
+    torch.cuda.synchronize()
+    now = env.state.to_host()
+    for f in STATE_FIELDS:
+        assert np.array_equal(now[f][mask == 0], snap[f][mask == 0]), f
+    assert (now['g_time'][mask == 1] == 0.25).all()
+
+
+def test_orca_act_matches_oracle(cuda_env, oracle):
+    for N, vis in [(5, 0), (20, 1)]:
+        B = 1000
+        host = _random_host_state(oracle, B, N, seed=3)
+        env = cuda_env(B, N, robot_visible=bool(vis), robot_policy='external_xy')
+        env.state.load_host(host)
+        snap = env.state.to_host()
+        act = env.orca_act().cpu().numpy()
+        ref = oracle.orca_act(oracle.default_params(robot_visible=vis), host)
+        assert np.array_equal(act, ref)
+        now = env.state.to_host()
+        for f in STATE_FIELDS:
+            assert np.array_equal(now[f], snap[f])
+
+
+def test_pack_and_lookahead_match_oracle_and_reference(cuda_env, oracle):
+    d = load_golden('rotate_lookahead')
+    actions = np.array([[float(x) for x in a] for a in d['action_space']])
+    rows = d['rows']
+    N = 5
+    host = fill_host_state(oracle, [r['scene'] for r in rows], N)
+    host.g_time[:] = [float(r['global_time']) for r in rows]
+    env = cuda_env(len(rows), N, robot_policy='external_xy')
+    env.state.load_host(host)
+    packed = env.pack_joint().cpu().numpy()
+    states, reward = env.lookahead_pack(torch.from_numpy(actions).to(env.device))
+    states = states.cpu().numpy(); reward = reward.cpu().numpy()
+    o_packed = oracle.pack_joint(host)
+    o_states, o_reward = oracle.lookahead_pack(oracle.default_params(robot_policy=0), host, actions)
+    assert np.array_equal(reward, o_reward)
+    assert np.abs(packed - o_packed).max() < 1e-5 and np.abs(states - o_states).max() < 1e-5
+    for e, r in enumerate(rows):      # the reference's own torch rotate / onestep_lookahead outputs
+        ref_cur = np.array([[float(v) for v in row] for row in r['rotated_current']], dtype=np.float32)
+        assert np.abs(packed[e] - ref_cur).max() < 1e-5
+        for k, la in enumerate(r['lookahead']):
+            assert reward[e, k] == float(la['reward'])
+            ref = np.array([[float(v) for v in row] for row in la['rotated']], dtype=np.float32)
+            assert np.abs(states[e, k] - ref).max() < 2e-5, (e, k)
+    # bigger random batch, N = 20 (tile path with many rows)
+    host = _random_host_state(oracle, 257, 20, seed=9)
+    env = cuda_env(257, 20, robot_visible=True, robot_policy='external_xy')
+    env.state.load_host(host)
+    states, reward = env.lookahead_pack(torch.from_numpy(actions).to(env.device))
+    o_states, o_reward = oracle.lookahead_pack(oracle.default_params(robot_visible=1, robot_policy=0), host, actions)
+    assert np.array_equal(reward.cpu().numpy(), o_reward)
+    assert np.abs(states.cpu().numpy() - o_states).max() < 1e-4
+
+
+def test_large_batch_linearity(cuda_env, oracle):
+    """BASELINE.json sizes (4096 and 131072/8 = 16384 envs): a batch built from 500 distinct scenes tiled must give,
+    for every copy, exactly the result of the 500-env batch (envs are independent -> size-independent property)."""
+    N = 5
+    cases = load_golden('suite_circle5_invisible')['cases']
+    base = fill_host_state(oracle, [c['init'] for c in cases], N)
+    small = cuda_env(500, N); small.state.load_host(base)
+    for B in (4096, 16384):
+        env = cuda_env(B, N)
+        idx = torch.arange(B, device=env.device) % 500
+        for f in env.state.FIELDS:
+            getattr(env.state, f).copy_(getattr(small.state, f)[idx])
+        s2 = cuda_env(500, N); s2.state.load_host(base)
+        for _ in range(20):
+            env.step(); s2.step()
+        torch.cuda.synchronize()
+        for f in ('h_pos', 'h_vel', 'r_pos', 'g_time'):
+            assert torch.equal(getattr(env.state, f), getattr(s2.state, f)[idx]), (B, f)
+        assert torch.equal(env.info, s2.info[idx]) and torch.equal(env.reward, s2.reward[idx])
