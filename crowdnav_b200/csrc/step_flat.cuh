@@ -1,0 +1,335 @@
+// step_flat.cuh -- CrowdSim step for small crowds (N <= 5 humans), register-resident ORCA solver.
+//
+// Same contract as step_kernel (crowd_sim/envs/crowd_sim.py:317-420 + orca.py:82-132 + explorer.py:41-72).
+// Mapping: one thread per (env, agent) solve, L = N + 1 lanes per env, floor(32 / L) whole envs per warp so an env
+// never straddles a warp: all intra-env exchange (candidate positions/velocities/radii for the neighbour scan, the
+// robot's position and action for the swept-segment test, the per-human clearances for the min / any reduction) is
+// done with warp shuffles -- no shared-memory staging, no block barrier on the common path.
+// The <= N ORCA lines of a solve live in REGISTERS: every loop over lines is fully unrolled (template on N), so
+// the LP code has static register indexing, no local/shared memory traffic and instruction-level parallelism
+// across the independent (i, j) line pairs.
+// linearProgram3 (needed by ~4.6 % of the solves, i.e. by some lane of ~3 of 4 warps) is NOT run in place: the
+// solves that need it are compacted into a block-level shared-memory queue and processed densely by the first
+// warp(s) of the block, so the expensive fallback is paid by few lanes instead of being serialised into every warp.
+//
+// Evidence that motivated this design (profiles/r01_*): one-thread-per-agent with shared-memory lines ran at 13.6/32
+// active lanes and 3480 instructions per warp; the warp-per-env cooperative variant needed 1750 warp instructions
+// per env. This kernel needs ~300 per env.
+#pragma once
+#include "crowdsim_common.cuh"
+
+namespace cs {
+
+#define CS_FULL 0xffffffffu
+
+template <int M> struct RegLines { orca::V2 p[M], d[M]; };
+
+// linearProgram1 on register lines; lines 0..line_no-1 constrain line `line_no`. `n_prev` = line_no (template-unrolled).
+template <int M>
+__device__ __forceinline__ bool lp1_reg(const RegLines<M> &R, const bool (&valid)[M], int line_no, orca::V2 lp, orca::V2 ld,
+                                        float radius, orca::V2 opt, bool dir_opt, orca::V2 &result)
+{
+    using namespace orca;
+    const float dp = dot(lp, ld);
+    const float disc = sqr(dp) + sqr(radius) - abssq(lp);
+    if (disc < 0.0f) return false;
+    const float sq = sqrtf(disc);
+    float t_left = -dp - sq, t_right = -dp + sq;
+    #pragma unroll
+    for (int j = 0; j < M - 1; ++j) {
+        if (j < line_no && valid[j]) {
+            const float den = det(ld, R.d[j]);
+            const float num = det(R.d[j], lp - R.p[j]);
+            if (fabsf(den) <= kEps) {
+                if (num < 0.0f) return false;
+            } else {
+                const float t = num / den;
+                if (den >= 0.0f) t_right = (t < t_right) ? t : t_right;
+                else             t_left = (t_left < t) ? t : t_left;
+                if (t_left > t_right) return false;
+            }
+        }
+    }
+    if (dir_opt) {
+        if (dot(opt, ld) > 0.0f) result = lp + t_right * ld;
+        else                     result = lp + t_left * ld;
+    } else {
+        const float t = dot(ld, opt - lp);
+        if (t < t_left)       result = lp + t_left * ld;
+        else if (t > t_right) result = lp + t_right * ld;
+        else                  result = lp + t * ld;
+    }
+    return true;
+}
+
+// linearProgram2 over positions 0..count-1 (positions with valid[i] == false hold no line). Returns failing position or count.
+template <int M>
+__device__ __forceinline__ int lp2_reg(const RegLines<M> &R, const bool (&valid)[M], int count, float radius, orca::V2 opt,
+                                       bool dir_opt, orca::V2 &result)
+{
+    using namespace orca;
+    if (dir_opt)                          result = mk(opt.x * radius, opt.y * radius);
+    else if (abssq(opt) > sqr(radius)) { const V2 nv = normalize(opt); result = mk(nv.x * radius, nv.y * radius); }
+    else                                  result = opt;
+    #pragma unroll
+    for (int i = 0; i < M; ++i) {
+        if (i < count && valid[i]) {
+            if (det(R.d[i], R.p[i] - result) > 0.0f) {
+                const V2 tmp = result;
+                if (!lp1_reg<M>(R, valid, i, R.p[i], R.d[i], radius, opt, dir_opt, result)) { result = tmp; return i; }
+            }
+        }
+    }
+    return count;
+}
+
+// linearProgram3 (numObstLines == 0) on register lines.
+// Note on i == 0 in lp3: RVO2's loop starts at beginLine, which can be 0 (line 0 alone infeasible with the speed disc).
+// Then projLines is empty, lp2 over zero lines returns 0 == size (no failure) and sets result = optVelocity * radius
+// with optVelocity = (-dir.y, dir.x); handled explicitly in lp3_entry below.
+template <int M>
+__device__ __forceinline__ void lp3_entry(const RegLines<M> &R, int n, int begin, float radius, orca::V2 &result)
+{
+    using namespace orca;
+    float distance0 = 0.0f;
+    if (begin == 0 && n > 0) {
+        if (det(R.d[0], R.p[0] - result) > 0.0f) {
+            // empty projected-line set: linearProgram2 just returns its initial point
+            result = mk(-R.d[0].y * radius, R.d[0].x * radius);
+            distance0 = det(R.d[0], R.p[0] - result);
+        }
+    }
+    // continue with i >= 1, carrying `distance`
+    float distance = distance0;
+    #pragma unroll
+    for (int i = 1; i < M; ++i) {
+        if (i >= begin && i < n) {
+            if (det(R.d[i], R.p[i] - result) > distance) {
+                RegLines<M> P; bool pv[M];
+                #pragma unroll
+                for (int j = 0; j < M; ++j) { pv[j] = false; P.p[j] = mk(0.f, 0.f); P.d[j] = mk(0.f, 0.f); }
+                #pragma unroll
+                for (int j = 0; j < M - 1; ++j) {
+                    if (j < i) {
+                        const float d = det(R.d[i], R.d[j]);
+                        bool ok = true; V2 pp = mk(0.f, 0.f);
+                        if (fabsf(d) <= kEps) {
+                            if (dot(R.d[i], R.d[j]) > 0.0f) ok = false;
+                            else pp = 0.5f * (R.p[i] + R.p[j]);
+                        } else {
+                            const float t = det(R.d[j], R.p[i] - R.p[j]) / d;
+                            pp = R.p[i] + t * R.d[i];
+                        }
+                        if (ok) { pv[j] = true; P.p[j] = pp; P.d[j] = normalize(R.d[j] - R.d[i]); }
+                    }
+                }
+                const V2 tmp = result;
+                if (lp2_reg<M>(P, pv, i, radius, mk(-R.d[i].y, R.d[i].x), true, result) < i) result = tmp;
+                distance = det(R.d[i], R.p[i] - result);
+            }
+        }
+    }
+}
+
+template <int N>
+__global__ void __launch_bounds__(128) step_flat_kernel(const __grid_constant__ StepArgs A)
+{
+    using namespace orca;
+    constexpr int L = N + 1, M = N, EPW = 32 / L, WPB = 4, T = 32 * WPB;
+    constexpr int QF = 4 * M + 5;                           // floats per queued lp3 work item
+    __shared__ float s_q[QF][T];                            // [field][slot]: conflict-free for consecutive slots
+    __shared__ float s_res[2][T];
+    __shared__ int s_qcount;
+
+    const KParams &k = A.k;
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    const int le = lane / L, a = lane - le * L;             // env within the warp, agent within the env
+    const int ebase = le * L;                               // first lane of my env
+    const int e = (blockIdx.x * WPB + wib) * EPW + le;
+    const bool is_robot = (a == N);
+    bool live = (le < EPW) && (e < A.B);
+    if (live && A.st.active) live = (A.st.active[e] != 0);
+    if (tid == 0) s_qcount = 0;
+
+    // ---- own agent: coalesced 16-byte loads ----
+    double2 pos = make_double2(0, 0), vel = pos, goal = pos, attr = make_double2(0.3, 1.0);
+    double theta = 0, gtime = 0; double2 ext = make_double2(0, 0);
+    if (live) {
+        if (!is_robot) {
+            const size_t i = (size_t)e * N + a;
+            pos = ld2(A.st.h_pos, i); vel = ld2(A.st.h_vel, i); goal = ld2(A.st.h_goal, i); attr = ld2(A.st.h_attr, i);
+        } else {
+            pos = ld2(A.st.r_pos, e); vel = ld2(A.st.r_vel, e); goal = ld2(A.st.r_goal, e); attr = ld2(A.st.r_attr, e);
+            gtime = A.st.g_time[e];
+            if (k.robot_policy == CROWDSIM_ROBOT_EXTERNAL_ROT) theta = A.st.r_theta[e];
+            if (k.robot_policy != CROWDSIM_ROBOT_ORCA) ext = ld2(A.io.action, e);
+        }
+    }
+    // float32 view of myself for the other lanes of my env (rvo2 boundary casts, orca.py:100-110)
+    const float fpx = (float)pos.x, fpy = (float)pos.y, fvx = (float)vel.x, fvy = (float)vel.y;
+    const float frh = (float)(attr.x + 0.01 + k.human_safety_space);     // my radius as seen by a human observer
+    const float frr = (float)(attr.x + 0.01 + k.robot_safety_space);     // ... by the robot
+    const bool solves = live && (!is_robot || k.robot_policy == CROWDSIM_ROBOT_ORCA);
+
+    // ---- orca.py:113-115 preferred velocity (float64) ----
+    const double gvx = goal.x - pos.x, gvy = goal.y - pos.y;
+    const double speed = norm2(gvx, gvy);
+    const V2 pref = mk((float)((speed > 1) ? gvx / speed : gvx), (float)((speed > 1) ? gvy / speed : gvy));
+    const V2 p = mk(fpx, fpy), v = mk(fvx, fvy);
+    const float r = is_robot ? frr : frh;
+    const float max_speed = (float)attr.y;
+
+    // ---- neighbour scan: candidate slot c -> agent j (reference order: other humans, then the robot iff visible) ----
+    float dsq[M]; bool inr[M]; int jj[M];
+    #pragma unroll
+    for (int c = 0; c < M; ++c) {
+        int j; bool cv;
+        if (is_robot) { j = c; cv = true; }
+        else if (c < N - 1) { j = (c < a) ? c : c + 1; cv = true; }
+        else { j = N; cv = (k.robot_visible != 0); }
+        jj[c] = j;
+        const float qx = __shfl_sync(CS_FULL, fpx, ebase + j), qy = __shfl_sync(CS_FULL, fpy, ebase + j);
+        dsq[c] = abssq(p - mk(qx, qy));
+        inr[c] = solves && cv && (k.max_neighbors > 0) && dsq[c] < sqr(k.neighbor_dist);
+    }
+    // rank of each candidate = position RVO2's insertion sort (strict <, ties in scan order) would give it
+    int nl = 0; int src[M];                 // src[kk] = agent index of the kk-th nearest
+    #pragma unroll
+    for (int kk = 0; kk < M; ++kk) src[kk] = 0;
+    #pragma unroll
+    for (int c = 0; c < M; ++c) {
+        int rank = 0;
+        #pragma unroll
+        for (int cc = 0; cc < M; ++cc)
+            if (cc != c && inr[cc] && (dsq[cc] < dsq[c] || (dsq[cc] == dsq[c] && cc < c))) ++rank;
+        if (inr[c]) {
+            ++nl;
+            #pragma unroll
+            for (int kk = 0; kk < M; ++kk) if (rank == kk) src[kk] = jj[c];
+        }
+    }
+    nl = nl < k.max_neighbors ? nl : k.max_neighbors;
+
+    // ---- ORCA lines in rank order, in registers ----
+    RegLines<M> R; bool valid[M];
+    #pragma unroll
+    for (int kk = 0; kk < M; ++kk) {
+        const int sl = ebase + src[kk];
+        const float qx = __shfl_sync(CS_FULL, fpx, sl), qy = __shfl_sync(CS_FULL, fpy, sl);
+        const float wx = __shfl_sync(CS_FULL, fvx, sl), wy = __shfl_sync(CS_FULL, fvy, sl);
+        const float rh = __shfl_sync(CS_FULL, frh, sl), rr = __shfl_sync(CS_FULL, frr, sl);
+        valid[kk] = kk < nl;
+        R.p[kk] = mk(0.f, 0.f); R.d[kk] = mk(0.f, 0.f);
+        if (valid[kk]) make_line(p, v, r, mk(qx, qy), mk(wx, wy), is_robot ? rr : rh, k.inv_time_horizon, k.inv_time_step, R.p[kk], R.d[kk]);
+    }
+
+    // ---- linear programs: lp2 in place, lp3 deferred to the block-compacted pass ----
+    V2 nv = mk(0.f, 0.f);
+    int fail = 0;
+    if (solves) fail = lp2_reg<M>(R, valid, nl, max_speed, pref, false, nv);
+    const bool need3 = solves && fail < nl;
+    __syncthreads();                                         // s_qcount = 0 visible
+    int slot = -1;
+    if (need3) {
+        slot = atomicAdd(&s_qcount, 1);
+        #pragma unroll
+        for (int kk = 0; kk < M; ++kk) {
+            s_q[4 * kk + 0][slot] = R.p[kk].x; s_q[4 * kk + 1][slot] = R.p[kk].y;
+            s_q[4 * kk + 2][slot] = R.d[kk].x; s_q[4 * kk + 3][slot] = R.d[kk].y;
+        }
+        s_q[4 * M + 0][slot] = __int_as_float(nl); s_q[4 * M + 1][slot] = __int_as_float(fail);
+        s_q[4 * M + 2][slot] = max_speed; s_q[4 * M + 3][slot] = nv.x; s_q[4 * M + 4][slot] = nv.y;
+    }
+    if (__syncthreads_or(need3 ? 1 : 0)) {
+        const int cnt = s_qcount;
+        if (tid < cnt) {                                     // dense: work item q is handled by thread q
+            RegLines<M> Q;
+            #pragma unroll
+            for (int kk = 0; kk < M; ++kk) { Q.p[kk] = mk(s_q[4 * kk + 0][tid], s_q[4 * kk + 1][tid]); Q.d[kk] = mk(s_q[4 * kk + 2][tid], s_q[4 * kk + 3][tid]); }
+            const int qn = __float_as_int(s_q[4 * M + 0][tid]), qf = __float_as_int(s_q[4 * M + 1][tid]);
+            const float qr = s_q[4 * M + 2][tid];
+            V2 res = mk(s_q[4 * M + 3][tid], s_q[4 * M + 4][tid]);
+            lp3_entry<M>(Q, qn, qf, qr, res);
+            s_res[0][tid] = res.x; s_res[1][tid] = res.y;
+        }
+        __syncthreads();
+        if (need3) nv = mk(s_res[0][slot], s_res[1][slot]);
+    }
+
+    // ---- robot velocity of this step, broadcast inside the env ----
+    double ax = 0, ay = 0, rvx = 0, rvy = 0;
+    if (is_robot) {
+        if (k.robot_policy == CROWDSIM_ROBOT_ORCA) { ax = (double)nv.x; ay = (double)nv.y; rvx = ax; rvy = ay; }
+        else if (k.robot_policy == CROWDSIM_ROBOT_EXTERNAL_ROT) { ax = ext.x; ay = ext.y; rvx = ax * cos(ay + theta); rvy = ax * sin(ay + theta); }
+        else { ax = ext.x; ay = ext.y; rvx = ax; rvy = ay; }
+    }
+    const int rl = ebase + N;                                // my env's robot lane
+    const double Rvx = __shfl_sync(CS_FULL, rvx, rl), Rvy = __shfl_sync(CS_FULL, rvy, rl);
+    const double Rpx = __shfl_sync(CS_FULL, pos.x, rl), Rpy = __shfl_sync(CS_FULL, pos.y, rl);
+    const double Rrad = __shfl_sync(CS_FULL, attr.x, rl);
+
+    // ---- human lanes: swept-segment clearance (crowd_sim.py:333-345) + Euler step (agent.py:122-135) ----
+    const double dt = k.time_step;
+    double closest = 0.0;
+    if (live && !is_robot) {
+        const double px = pos.x - Rpx, py = pos.y - Rpy;
+        const double vx = vel.x - Rvx, vy = vel.y - Rvy;
+        const double ex = px + vx * dt, ey = py + vy * dt;
+        closest = point_to_segment_dist0(px, py, ex, ey) - attr.x - Rrad;
+        const double hx = (double)nv.x, hy = (double)nv.y;
+        const size_t i = (size_t)e * N + a;
+        st2(A.st.h_pos, i, make_double2(pos.x + hx * dt, pos.y + hy * dt));
+        st2(A.st.h_vel, i, make_double2(hx, hy));
+    }
+    // ordered fold over the env's humans (first collision breaks, crowd_sim.py:346-351); consumed by the robot lane
+    double dmin = __longlong_as_double(0x7ff0000000000000LL); bool collision = false;
+    #pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double ci = __shfl_sync(CS_FULL, closest, ebase + i);
+        if (!collision) { if (ci < 0) collision = true; else if (ci < dmin) dmin = ci; }
+    }
+    if (!live || !is_robot) return;
+
+    // ---- robot lane: ladder, update, bookkeeping ----
+    double npx, npy, nvx, nvy;
+    if (k.robot_policy != CROWDSIM_ROBOT_EXTERNAL_ROT) { npx = pos.x + ax * dt; npy = pos.y + ay * dt; nvx = ax; nvy = ay; }
+    else { const double th = theta + ay; npx = pos.x + cos(th) * ax * dt; npy = pos.y + sin(th) * ax * dt; nvx = nvy = 0; }
+    const bool reaching_goal = norm2(npx - goal.x, npy - goal.y) < attr.x;
+    double reward; bool done; int info;
+    if (gtime >= k.time_limit - 1) { reward = 0; done = true; info = CROWDSIM_INFO_TIMEOUT; }
+    else if (collision) { reward = k.collision_penalty; done = true; info = CROWDSIM_INFO_COLLISION; }
+    else if (reaching_goal) { reward = k.success_reward; done = true; info = CROWDSIM_INFO_REACHGOAL; }
+    else if (dmin < k.discomfort_dist) { reward = (dmin - k.discomfort_dist) * k.discomfort_penalty_factor * dt; done = false; info = CROWDSIM_INFO_DANGER; }
+    else { reward = 0; done = false; info = CROWDSIM_INFO_NOTHING; }
+    if (k.robot_policy == CROWDSIM_ROBOT_EXTERNAL_ROT) {
+        double nth = fmod(theta + ay, 2 * CS_PI); if (nth < 0) nth += 2 * CS_PI;
+        A.st.r_theta[e] = nth; nvx = ax * cos(nth); nvy = ax * sin(nth);
+    }
+    st2(A.st.r_pos, e, make_double2(npx, npy));
+    st2(A.st.r_vel, e, make_double2(nvx, nvy));
+    const double ntime = gtime + dt;
+    A.st.g_time[e] = ntime;
+    if (A.io.action_out) st2(A.io.action_out, e, make_double2(nvx, nvy));
+    A.io.reward[e] = reward; A.io.dmin[e] = dmin; A.io.done[e] = done ? 1 : 0; A.io.info[e] = (uint8_t)info;
+    if (A.has_ep) {
+        const crowdsim_episodes &ep = A.ep;
+        const int t = ep.ep_steps[e];
+        const double disc = (t < ep.discount_len) ? ep.discount[t] : 0.0;
+        const double ret = ep.ep_return[e] + disc * reward;
+        int tc = ep.ep_too_close[e]; double mds = ep.ep_min_dist_sum[e];
+        if (info == CROWDSIM_INFO_DANGER) { tc += 1; mds += dmin; ep.ep_too_close[e] = tc; ep.ep_min_dist_sum[e] = mds; }
+        ep.ep_return[e] = ret; ep.ep_steps[e] = t + 1;
+        if (done) {
+            const int cs_ = ep.ep_case[e];
+            if (cs_ >= 0) {
+                ep.res_info[cs_] = (uint8_t)info; ep.res_steps[cs_] = t + 1;
+                ep.res_time[cs_] = (info == CROWDSIM_INFO_TIMEOUT) ? k.time_limit : ntime;
+                ep.res_return[cs_] = ret; ep.res_too_close[cs_] = tc; ep.res_min_dist_sum[cs_] = mds;
+                if (ep.res_final_rpos) st2(ep.res_final_rpos, cs_, make_double2(npx, npy));
+            }
+            if (A.st.active) A.st.active[e] = 0;
+        }
+    }
+}
+
+}  // namespace cs

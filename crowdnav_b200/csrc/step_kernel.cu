@@ -17,6 +17,7 @@
 namespace cs {
 
 unsigned long long g_launches = 0;
+int g_force_generic = 0;   // test hook: route every N through the generic one-thread-per-agent kernel
 
 struct StepArgs {
     KParams k;
@@ -27,6 +28,10 @@ struct StepArgs {
     int has_ep;
     int act_only;      // crowdsim_orca_act: robot lanes solve and write action_out, nothing is mutated
 };
+
+}  // namespace cs
+#include "step_flat.cuh"
+namespace cs {
 
 __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepArgs A)
 {
@@ -177,6 +182,20 @@ static int launch(const crowdsim_params *prm, int B, int N, const crowdsim_state
     A.B = B; A.N = N; A.L = N + 1; A.EPB = envs_per_block(A.L, 128);
     A.st = *st; A.io = *io; A.has_ep = (ep != nullptr && !act_only); A.act_only = act_only;
     if (A.has_ep) A.ep = *ep; else memset(&A.ep, 0, sizeof(A.ep));
+    if (!act_only && N >= 1 && N <= 5 && !g_force_generic) {
+        // small crowds: register-resident solver, whole envs per warp, block-compacted lp3 (step_flat.cuh)
+        const int epb = 4 * (32 / (N + 1));
+        const int blocks = (B + epb - 1) / epb;
+        switch (N) {
+            case 1: step_flat_kernel<1><<<blocks, 128, 0, stream>>>(A); break;
+            case 2: step_flat_kernel<2><<<blocks, 128, 0, stream>>>(A); break;
+            case 3: step_flat_kernel<3><<<blocks, 128, 0, stream>>>(A); break;
+            case 4: step_flat_kernel<4><<<blocks, 128, 0, stream>>>(A); break;
+            default: step_flat_kernel<5><<<blocks, 128, 0, stream>>>(A); break;
+        }
+        ++g_launches;
+        return (int)cudaGetLastError();
+    }
     const int threads = A.EPB * A.L;
     const int blocks = (B + A.EPB - 1) / A.EPB;
     const size_t smem = stage_bytes(A.EPB, A.L, A.k.nb_alloc, threads);
@@ -203,6 +222,8 @@ extern "C" int crowdsim_orca_act(const crowdsim_params *prm, int B, int N, const
     crowdsim_step_io io; memset(&io, 0, sizeof(io)); io.action_out = action_out;
     return cs::launch(prm, B, N, st, &io, nullptr, 1, (cudaStream_t)stream);
 }
+
+extern "C" void crowdsim_debug_force_generic(int on) { cs::g_force_generic = on; }
 
 extern "C" int crowdsim_abi_version(void) { return CROWDSIM_ABI_VERSION; }
 

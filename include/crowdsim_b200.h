@@ -150,6 +150,9 @@ int crowdsim_abi_version(void);
 int crowdsim_device_check(int *sm_count, int *cc_major, int *cc_minor);
 /* Kernels launched by this library since load (the bench's gpu_launches claim). */
 unsigned long long crowdsim_launch_count(void);
+/* Test hook: 1 = use the generic one-thread-per-agent step kernel for every N (default 0: N <= 5 uses the
+ * register-resident small-crowd kernel). Both are held to the same bit-exact parity bar. */
+void crowdsim_debug_force_generic(int on);
 
 /* One lockstep env-step for B envs. `ep` may be NULL. */
 int crowdsim_step(const crowdsim_params *prm, int B, int N, crowdsim_state *st, crowdsim_step_io *io,

@@ -24,7 +24,7 @@ def lib():
 def test_exports_every_declared_symbol(lib):
     from crowdnav_b200 import _abi
     src = open(HEADER).read()
-    declared = set(re.findall(r'^\s*(?:int|unsigned long long)\s+(crowdsim_\w+)\s*\(', src, re.M))
+    declared = set(re.findall(r'^\s*(?:int|void|unsigned long long)\s+(crowdsim_\w+)\s*\(', src, re.M))
     assert declared == set(_abi.EXPORTS), declared ^ set(_abi.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name

@@ -67,10 +67,22 @@ def test_step_reproduces_golden_trajectories(cuda_env, oracle, name):
             assert (dev['r_pos'][e] == r[0:2]).all() and (dev['h_pos'][e] == h[:, 0:2]).all() and (dev['h_vel'][e] == h[:, 2:4]).all()
 
 
-@pytest.mark.parametrize('N,vis,policy', [(5, 0, 'orca'), (5, 1, 'orca'), (1, 0, 'orca'), (2, 1, 'external_xy'),
-                                          (10, 1, 'orca'), (11, 0, 'orca'), (20, 0, 'orca'), (20, 1, 'external_xy'),
-                                          (33, 1, 'orca'), (63, 1, 'orca'), (0, 0, 'orca'), (5, 0, 'external_rot')])
-def test_step_random_scenes_bit_exact(cuda_env, oracle, N, vis, policy):
+@pytest.fixture(autouse=True)
+def _default_kernel_routing():
+    """Every test starts with the default routing (N <= 5 -> warp-cooperative kernel)."""
+    from crowdnav_b200 import _abi
+    _abi.load().crowdsim_debug_force_generic(0)
+    yield
+    _abi.load().crowdsim_debug_force_generic(0)
+
+
+@pytest.mark.parametrize('N,vis,policy,generic', [
+    (5, 0, 'orca', 0), (5, 1, 'orca', 0), (5, 0, 'external_xy', 0), (5, 1, 'external_xy', 0), (4, 1, 'orca', 0), (3, 0, 'orca', 0),
+    (2, 1, 'external_xy', 0), (2, 0, 'orca', 0), (1, 0, 'orca', 0), (1, 1, 'orca', 0), (5, 0, 'external_rot', 0),
+    (5, 0, 'orca', 1), (5, 1, 'orca', 1), (1, 0, 'orca', 1), (2, 1, 'external_xy', 1), (5, 0, 'external_rot', 1),
+    (10, 1, 'orca', 0), (11, 0, 'orca', 0), (20, 0, 'orca', 0), (20, 1, 'external_xy', 0), (33, 1, 'orca', 0), (63, 1, 'orca', 0),
+    (0, 0, 'orca', 0), (6, 1, 'orca', 0)])
+def test_step_random_scenes_bit_exact(cuda_env, oracle, N, vis, policy, generic):
     """Dense random scenes (many overlapping agents -> collision branch, lp3 fallback, 10-of-N truncation),
     8 consecutive steps, every state/output array compared for equality with the CPU oracle."""
     B = 1500 if N <= 20 else 300
@@ -78,6 +90,7 @@ def test_step_random_scenes_bit_exact(cuda_env, oracle, N, vis, policy):
     env = cuda_env(B, N, robot_visible=bool(vis), robot_policy=policy)
     env.state.load_host(host)
     from crowdnav_b200 import _abi
+    _abi.load().crowdsim_debug_force_generic(generic)
     prm = oracle.default_params(robot_visible=vis, robot_policy={'orca': _abi.ROBOT_ORCA, 'external_xy': _abi.ROBOT_EXTERNAL_XY,
                                                                  'external_rot': _abi.ROBOT_EXTERNAL_ROT}[policy])
     io = oracle.HostStepIO(B)
@@ -104,14 +117,17 @@ def test_step_random_scenes_bit_exact(cuda_env, oracle, N, vis, policy):
             _assert_io_equal(env, io, what='N=%d step %d' % (N, t))
 
 
+@pytest.mark.parametrize('generic', [0, 1])
 @pytest.mark.parametrize('name', sorted(SUITES))
-def test_full_suites_from_reference_scenes(cuda_env, oracle, name):
+def test_full_suites_from_reference_scenes(cuda_env, oracle, name, generic):
     """Whole episodes on the GPU from the reference's own initial scenes: terminal class, step count, time, discounted
     return, danger statistics and final positions identical to the reference's Python for every test case."""
     N, rule, vis, rand = SUITES[name]
     cases = load_golden('suite_' + name)['cases']
     B = len(cases)
     host = fill_host_state(oracle, [c['init'] for c in cases], N)
+    from crowdnav_b200 import _abi
+    _abi.load().crowdsim_debug_force_generic(generic)
     env = cuda_env(B, N, rule, robot_visible=bool(vis))
     ep = env.track_episodes(B)
     env.state.load_host(host)
@@ -155,7 +171,9 @@ def test_full_suites_device_reset(cuda_env, name):
 def test_reset_matches_oracle(cuda_env, oracle):
     worst = 0
     for N, rule, rand in [(5, 'circle_crossing', False), (5, 'square_crossing', False), (20, 'square_crossing', False),
-                          (10, 'circle_crossing', True), (5, 'square_crossing', True)]:
+                          (5, 'circle_crossing', True), (10, 'circle_crossing', False), (5, 'square_crossing', True)]:
+        # NB: keep the packing feasible -- 10 humans with random radii up to 0.5 cannot all keep 1.2 m from each
+        # other's starts AND goals on the r = 4 circle; the reference's rejection sampling would spin forever too.
         B = 2000
         seeds = np.concatenate([np.arange(1000, 1500), np.arange(2000, 3000), [0, 1, 99, 4294967295, 4294965295],
                                 np.random.RandomState(1).randint(0, 2 ** 32, B - 1505, dtype=np.uint64)]).astype(np.uint64)
@@ -168,12 +186,16 @@ def test_reset_matches_oracle(cuda_env, oracle):
         for f in ('h_attr', 'r_pos', 'r_goal', 'r_attr', 'r_vel', 'h_vel', 'g_time', 'r_theta'):
             assert np.array_equal(dev[f], getattr(host, f)), f
         for f in ('h_pos', 'h_goal'):
-            d = ulp_diff(dev[f], getattr(host, f)).max()
-            worst = max(worst, int(d))
-            assert d <= 4, (N, rule, f, d)
+            # px = 4*cos(angle) + noise: CUDA's cos/sin are within 1-2 ulp of glibc's, i.e. <= ~2e-15 absolute on
+            # |4 cos| <= 4 (cancellation against the noise term makes a relative/ulp bound meaningless)
+            d = np.abs(dev[f] - getattr(host, f)).max()
+            worst = max(worst, float(d))
+            assert d <= 4e-15, (N, rule, f, d)
+            frac_exact = float((dev[f] == getattr(host, f)).mean())
+            print('%s N=%d %s: %.1f%% of coordinates bit-identical, max abs diff %.2e' % (rule, N, f, 100 * frac_exact, d))
         if rule == 'square_crossing':        # no cos/sin on this path: bit-exact
             assert np.array_equal(dev['h_pos'], host.h_pos) and np.array_equal(dev['h_goal'], host.h_goal)
-    print('worst ulp distance of initial coordinates:', worst)
+    print('worst abs difference of initial coordinates:', worst)
 
 
 def test_reset_mask_and_active(cuda_env, oracle):
