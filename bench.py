@@ -214,19 +214,33 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # The whole timed region is ONE CUDA graph of K steps (2K kernel nodes, a single dependent chain on one stream):
+    # Python/ctypes launch overhead (~20 us per call) would otherwise dominate a 4096-env step.
+    side = torch.cuda.Stream(device=dev)
     it = 0
-    for _ in range(max(W, 3)):
-        step_pool(envs[it % pools]); it += 1
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step_pool(envs[it % pools]); it += 1
+    torch.cuda.synchronize()
+
+    def capture(n_steps, fn):
+        nonlocal it
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(n_steps):
+                fn(envs[it % pools]); it += 1
+        return g
+    g_warm = capture(max(W, 3), step_pool)
+    g_timed = capture(K, step_pool)
+    g_warm.replay()
     barrier()
     sampler = ClockSampler(local); sampler.start()
-    l0 = lib.crowdsim_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(K):
-        step_pool(envs[it % pools]); it += 1
+    g_timed.replay()
     e1.record()
     barrier()
-    launches = lib.crowdsim_launch_count() - l0
+    launches = 2 * K
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -235,57 +249,55 @@ def run_ours(args):
     ms_max = float(t.item())
     value = world * B * K / (ms_max * 1e-3)
 
-    # ---- roofline of the dominant kernel: CUDA events around each step-kernel launch, live, same rotating pools ----
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(K, 200))]
-    for a, b in kev:
-        env = envs[it % pools]; it += 1
-        a.record(); env.step(); b.record()
-        env.reset_seeds(mask=env.done, rule=args.rule, seed_stride=env.seed_stride)
-    torch.cuda.synchronize()
-    kms = sorted(a.elapsed_time(b) for a, b in kev)
-    k_avg = sum(kms) / len(kms)
+    # ---- roofline of the dominant kernel (the step kernel): a graph of one step launch per pool, no resets in between,
+    # replayed R times; CUDA events on the launching stream; per-launch duration = elapsed / (R * pools). The pools
+    # rotate, so each launch reads its state from HBM, not L2. ----
+    def step_only(env):
+        ep, env.episodes = env.episodes, None        # no episode bookkeeping -> finished envs keep stepping (same work)
+        env.step()
+        env.episodes = ep
+    g_step = capture(pools, step_only)
+    g_step.replay(); torch.cuda.synchronize()
+    R = max(3, min(20, 1200 // pools))
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(R):
+        g_step.replay()
+    k1.record(); torch.cuda.synchronize()
+    k_avg = k0.elapsed_time(k1) / (R * pools)
     peak, peak_src = load_peaks()
     achieved = B * bytes_per_env / (k_avg * 1e-3) / 1e9
-    roofline = {'bound': 'hbm', 'kernel': 'cs::step_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
-                'algorithmic_bytes_per_launch': B * bytes_per_env, 'avg_launch_us': 1e3 * k_avg, 'median_launch_us': 1e3 * kms[len(kms) // 2]}
+    roofline = {'bound': 'hbm', 'kernel': 'cs::step_flat_kernel' if N <= 5 else 'cs::step_kernel', 'achieved': achieved, 'peak': peak,
+                'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': B * bytes_per_env, 'avg_launch_us': 1e3 * k_avg,
+                'how': 'CUDA events around %d replays of a graph of %d back-to-back step launches (one per rotating batch)' % (R, pools)}
+    for env in envs:                                  # re-seed everything the step-only pass ran past its terminal state
+        env.reset_seeds(rule=args.rule, seed_stride=env.seed_stride)
+    torch.cuda.synchronize()
 
-    # ---- e2e: the public API with HOST buffers; H2D of the step's robot actions and D2H of its results, every step ----
+    # ---- e2e: the public host-facing API (HostStepper.step): pinned HOST buffers in and out every step. The robot is
+    # driven from the host like the reference's Explorer loop does it: action up, obs/reward/done/info (+ the robot's
+    # next ORCA decision) down, host waits for the results before the next step. ----
+    from crowdnav_b200.batched import HostStepper
     env = envs[0]
     env.set_robot_policy('external_xy')
-    h_act = torch.zeros((B, 2), dtype=torch.float64).pin_memory()
-    h_out = {k: torch.empty_like(v, device='cpu').pin_memory() for k, v in
-             (('h_pos', env.state.h_pos), ('h_vel', env.state.h_vel), ('reward', env.reward), ('done', env.done),
-              ('info', env.info), ('next_action', env.action_out))}
-    d_act = torch.zeros((B, 2), dtype=torch.float64, device=dev)
-    d_next = torch.zeros((B, 2), dtype=torch.float64, device=dev)
-    env.orca_act(d_next); h_act.copy_(d_next); torch.cuda.synchronize()
-
-    def e2e_step():
-        d_act.copy_(h_act, non_blocking=True)                      # H2D: this step's robot actions
-        env.step(d_act)
-        env.reset_seeds(mask=env.done, rule=args.rule, seed_stride=env.seed_stride)
-        env.orca_act(d_next)                                       # next decision of the (ORCA) robot policy
-        h_out['h_pos'].copy_(env.state.h_pos, non_blocking=True)   # D2H: observation, reward, done, info, next action
-        h_out['h_vel'].copy_(env.state.h_vel, non_blocking=True)
-        h_out['reward'].copy_(env.reward, non_blocking=True); h_out['done'].copy_(env.done, non_blocking=True)
-        h_out['info'].copy_(env.info, non_blocking=True); h_act.copy_(d_next, non_blocking=True)
-        torch.cuda.current_stream().synchronize()                  # the host reads the results before the next step
+    stepper = HostStepper(env, auto_reset_rule=args.rule, seed_stride=env.seed_stride, next_orca_action=True)
+    stepper.step()
     for _ in range(5):
-        e2e_step()
+        stepper.h_action.copy_(stepper.h_next_action); stepper.step()
     barrier()
+    ke = min(K, 400)
     t0 = time.perf_counter()
-    ke = min(K, 300)
     for _ in range(ke):
-        e2e_step()
-    torch.cuda.synchronize()
+        stepper.h_action.copy_(stepper.h_next_action)      # host-side "policy": apply the decision the device computed
+        stepper.step()
     e2e_dt = time.perf_counter() - t0
     t = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * ke / float(t.item())
-    h2d = h_act.numel() * 8
-    d2h = sum(v.numel() * v.element_size() for v in h_out.values())
+    h2d, d2h = stepper.h2d_bytes, stepper.d2h_bytes
+    launches_note = 'timed region: %d step + %d reset kernel launches (one CUDA graph)' % (K, K)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -300,9 +312,9 @@ def run_ours(args):
                 'config': {'workload': '%d batched envs x %d ORCA humans, %s, ORCA robot (invisible), auto-reset, per GPU' % (B, N, args.rule),
                            'envs_per_gpu': B, 'humans': N, 'l2': 'inputs larger than L2: %d rotating independent batches = %.0f MB of state' % (pools, pools * B * bytes_per_env / 1e6),
                            'parallelism': 'independent envs sharded over %d GPU(s), no data-path collective' % world},
-                'clocks': clocks, 'gpu_launches': int(launches),
+                'clocks': clocks, 'gpu_launches': int(launches), 'gpu_launches_note': launches_note,
                 'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                        'steps': ke, 'note': 'host pinned buffers <-> device every step; robot action uploaded, obs/reward/done/info/next-action downloaded'},
+                        'steps': ke, 'note': 'HostStepper.step(): pinned host buffers <-> device every step (one graph replay + stream sync per step); robot action uploaded, obs/reward/done/info/next ORCA action downloaded'},
                 'roofline': roofline, 'cpu_baseline': cpu}
         print(json.dumps(line))
     if world > 1:

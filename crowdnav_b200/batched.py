@@ -255,6 +255,58 @@ class BatchedCrowdSim(object):
         return out_states, out_reward
 
 
+class HostStepper(object):
+    """env.step() for callers that live on the host (the reference's calling convention: the policy hands a robot
+    action to env.step and gets observation, reward, done, info back -- crowd_nav/utils/explorer.py:42-43).
+
+    One call = one CUDA graph replay: H2D copy of the robot actions from pinned memory, the fused step kernel,
+    on-device regeneration of finished envs' scenes (optional), the robot's next ORCA decision (optional, so a host
+    loop can drive an ORCA robot), D2H copies of everything a caller reads, then a stream synchronise.
+    Buffers: self.h_action [B][2] (write before step()); results in self.h_pos, h_vel [B][N][2], h_reward, h_done,
+    h_info [B], h_next_action [B][2] (pinned torch tensors; .numpy() views are free)."""
+
+    def __init__(self, env, auto_reset_rule=None, seed_stride=0, next_orca_action=True):
+        self.env = env
+        B, N, dev = env.B, env.human_num, env.device
+        pin = lambda *shape, dtype=torch.float64: torch.zeros(shape, dtype=dtype).pin_memory()  # noqa: E731
+        self.h_action = pin(B, 2)
+        self.h_pos, self.h_vel = pin(B, N, 2), pin(B, N, 2)
+        self.h_reward = pin(B); self.h_done = pin(B, dtype=torch.uint8); self.h_info = pin(B, dtype=torch.uint8)
+        self.h_next_action = pin(B, 2)
+        self.d_action = torch.zeros((B, 2), dtype=torch.float64, device=dev)
+        self.d_next = torch.zeros((B, 2), dtype=torch.float64, device=dev)
+        self.stream = torch.cuda.Stream(device=dev)
+        self.h2d_bytes = self.h_action.numel() * 8
+        self.d2h_bytes = sum(t.numel() * t.element_size() for t in (self.h_pos, self.h_vel, self.h_reward, self.h_done, self.h_info))
+        if next_orca_action:
+            self.d2h_bytes += self.h_next_action.numel() * 8
+        self.kernels_per_step = 1 + (1 if auto_reset_rule else 0) + (1 if next_orca_action else 0)
+
+        def body():
+            self.d_action.copy_(self.h_action, non_blocking=True)
+            env.step(self.d_action)
+            if auto_reset_rule:
+                env.reset_seeds(mask=env.done, rule=auto_reset_rule, seed_stride=seed_stride)
+            if next_orca_action:
+                env.orca_act(self.d_next)
+                self.h_next_action.copy_(self.d_next, non_blocking=True)
+            self.h_pos.copy_(env.state.h_pos, non_blocking=True); self.h_vel.copy_(env.state.h_vel, non_blocking=True)
+            self.h_reward.copy_(env.reward, non_blocking=True); self.h_done.copy_(env.done, non_blocking=True)
+            self.h_info.copy_(env.info, non_blocking=True)
+        with torch.cuda.stream(self.stream):
+            body()                                     # warm-up outside capture (lazy inits)
+        self.stream.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=self.stream):
+            body()
+
+    def step(self):
+        with torch.cuda.stream(self.stream):
+            self.graph.replay()
+        self.stream.synchronize()
+        return (self.h_pos, self.h_vel), self.h_reward, self.h_done, self.h_info
+
+
 def default_config(human_num=5, test_sim='circle_crossing', train_val_sim='circle_crossing', robot_visible=False,
                    randomize_attributes=False):
     """The reference's crowd_nav/configs/env.config:1-37 as a RawConfigParser (values restated, not read from disk)."""

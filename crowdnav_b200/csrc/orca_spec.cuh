@@ -1,0 +1,176 @@
+// orca_spec.cuh -- "speculative" formulation of RVO2's incremental 2-D linear programs for small line counts (M <= 5),
+// written for SIMT execution: straight-line, select-based code with independent dependency chains.
+//
+// Observation that makes it possible (RVO2 linearProgram1/2/3):
+//   linearProgram1(lines, i, radius, opt, dirOpt, result) never READS `result`: the feasible interval [tLeft, tRight]
+//   on line i is determined by lines 0..i-1 and the speed disc, and the returned point is the point of that interval
+//   closest to `opt` (or its extreme in direction `opt`). The running result only enters linearProgram2 through the
+//   violation test det(dir_i, point_i - result) > 0 that decides WHETHER lp1 is called for line i.
+// So for every line i we can compute, up front and independently,
+//       feas_i  = "lp1(i) would succeed"            cand_i = "the point lp1(i) would return"
+// with exactly the operations (and operation order) lp1 would execute, and linearProgram2 collapses into a scan
+//       for i: if (violated_i(result)) { if (!feas_i) fail at i; else result = cand_i; }
+// The early exits of lp1's loop do not change the outcome: tLeft only grows and tRight only shrinks, so "tLeft >
+// tRight after some prefix" == "tLeft > tRight at the end"; a parallel line with negative numerator fails regardless
+// of where it is met; min/max folds are done in the same j order. Results are therefore bit-identical to the
+// sequential code (parity tests compare every velocity for equality), while a warp of 32 different solves executes
+// one common instruction stream with M(M-1)/2 independent divisions in flight instead of the union of 32 divergent
+// control paths.
+// The same holds for linearProgram3: the projected lines of (i, j) depend only on the lines, and the lp1 candidates of
+// the projected problems depend only on those; only two short scans are sequential.
+#pragma once
+#include "orca_device.cuh"
+
+namespace orca {
+
+template <int M> struct RegLines { V2 p[M], d[M]; };
+
+// One ORCA half-plane, both non-colliding branches evaluated and selected (the already-overlapping case, 0.09 % of
+// lines, stays a real branch). Operation order inside each branch is RVO2's (make_line in orca_device.cuh).
+__device__ __forceinline__ void make_line_sel(V2 p, V2 v, float r, V2 po, V2 vo, float ro, float inv_th, float inv_dt,
+                                              V2 &point, V2 &dir)
+{
+    const V2 rel_pos = po - p;
+    const V2 rel_vel = v - vo;
+    const float dist_sq = abssq(rel_pos);
+    const float comb_r = r + ro;
+    const float comb_r_sq = sqr(comb_r);
+    V2 u;
+    if (dist_sq > comb_r_sq) {
+        const V2 w = rel_vel - inv_th * rel_pos;
+        const float w_len_sq = abssq(w);
+        const float dot1 = dot(w, rel_pos);
+        // cut-off circle
+        const float w_len = sqrtf(w_len_sq);
+        const V2 unit_w = vdiv(w, w_len);
+        const V2 dir_c = mk(unit_w.y, -unit_w.x);
+        const V2 u_c = (comb_r * inv_th - w_len) * unit_w;
+        // legs
+        const float leg = sqrtf(dist_sq - comb_r_sq);
+        const bool left = det(rel_pos, w) > 0.0f;
+        const V2 num_l = mk(rel_pos.x * leg - rel_pos.y * comb_r, rel_pos.x * comb_r + rel_pos.y * leg);
+        const V2 num_r = mk(rel_pos.x * leg + rel_pos.y * comb_r, -rel_pos.x * comb_r + rel_pos.y * leg);
+        const V2 q = vdiv(left ? num_l : num_r, dist_sq);
+        const V2 dir_l = left ? q : -q;
+        const float dot2 = dot(rel_vel, dir_l);
+        const V2 u_l = dot2 * dir_l - rel_vel;
+        const bool cutoff = dot1 < 0.0f && sqr(dot1) > comb_r_sq * w_len_sq;
+        dir = cutoff ? dir_c : dir_l;
+        u = cutoff ? u_c : u_l;
+    } else {
+        const V2 w = rel_vel - inv_dt * rel_pos;
+        const float w_len = sqrtf(abssq(w));
+        const V2 unit_w = vdiv(w, w_len);
+        dir = mk(unit_w.y, -unit_w.x);
+        u = (comb_r * inv_dt - w_len) * unit_w;
+    }
+    point = v + 0.5f * u;
+}
+
+// lp1 candidates of every position (speculative). valid[i]: position i holds a line (absent positions never constrain).
+// CNT = number of leading positions to evaluate (compile time, <= M).
+template <int M, int CNT>
+__device__ __forceinline__ void lp1_all(const RegLines<M> &R, const bool (&valid)[M], float radius, V2 opt, bool dir_opt,
+                                        V2 (&cand)[M], bool (&feas)[M])
+{
+    #pragma unroll
+    for (int i = 0; i < CNT; ++i) {
+        const V2 lp = R.p[i], ld = R.d[i];
+        const float dp = dot(lp, ld);
+        const float disc = sqr(dp) + sqr(radius) - abssq(lp);
+        const float sq = sqrtf(disc);
+        float t_left = -dp - sq, t_right = -dp + sq;
+        bool bad = disc < 0.0f;
+        #pragma unroll
+        for (int j = 0; j < i; ++j) {
+            const float den = det(ld, R.d[j]);
+            const float num = det(R.d[j], lp - R.p[j]);
+            const bool use = valid[j];
+            const bool par = fabsf(den) <= kEps;
+            const float t = num / den;
+            bad = bad || (use && par && num < 0.0f);
+            const bool right = use && !par && den >= 0.0f, leftb = use && !par && den < 0.0f;
+            t_right = (right && t < t_right) ? t : t_right;          // std::min(tRight, t)
+            t_left = (leftb && t_left < t) ? t : t_left;             // std::max(tLeft, t)
+        }
+        feas[i] = !bad && !(t_left > t_right);
+        if (dir_opt) {
+            cand[i] = (dot(opt, ld) > 0.0f) ? (lp + t_right * ld) : (lp + t_left * ld);
+        } else {
+            const float t = dot(ld, opt - lp);
+            const float tc = (t < t_left) ? t_left : ((t > t_right) ? t_right : t);
+            cand[i] = lp + tc * ld;
+        }
+    }
+}
+
+// linearProgram2 as a scan over precomputed candidates. Returns the failing position or count.
+template <int M, int CNT>
+__device__ __forceinline__ int lp2_scan(const RegLines<M> &R, const bool (&valid)[M], int count, const V2 (&cand)[M], const bool (&feas)[M],
+                                        V2 init, V2 &result)
+{
+    result = init;
+    int fail = count;
+    #pragma unroll
+    for (int i = 0; i < CNT; ++i) {
+        const bool viol = (i < count) && (fail == count) && valid[i] && det(R.d[i], R.p[i] - result) > 0.0f;
+        if (viol) { if (!feas[i]) fail = i; else result = cand[i]; }
+    }
+    return fail;
+}
+
+// Initial point of linearProgram2 (closest-point mode).
+__device__ __forceinline__ V2 lp2_init(V2 opt, float radius)
+{
+    if (abssq(opt) > sqr(radius)) { const V2 nv = normalize(opt); return mk(nv.x * radius, nv.y * radius); }
+    return opt;
+}
+
+// One outer iteration (line I) of linearProgram3: projected lines of (I, j < I), their lp1 candidates, then the scan.
+template <int M, int I>
+__device__ __forceinline__ void lp3_iter(const RegLines<M> &R, int n, int begin, float radius, V2 &result, float &distance)
+{
+    RegLines<M> P; bool pv[M];
+    const V2 oi = mk(-R.d[I].y, R.d[I].x);
+    #pragma unroll
+    for (int j = 0; j < M; ++j) { pv[j] = false; P.p[j] = mk(0.f, 0.f); P.d[j] = mk(0.f, 0.f); }
+    #pragma unroll
+    for (int j = 0; j < I; ++j) {
+        const float d = det(R.d[I], R.d[j]);
+        const bool par = fabsf(d) <= kEps;
+        const float t = det(R.d[j], R.p[I] - R.p[j]) / d;
+        const V2 pp_par = 0.5f * (R.p[I] + R.p[j]);
+        const V2 pp_gen = R.p[I] + t * R.d[I];
+        pv[j] = !(par && dot(R.d[I], R.d[j]) > 0.0f);
+        P.p[j] = par ? pp_par : pp_gen;
+        P.d[j] = normalize(R.d[j] - R.d[I]);
+    }
+    V2 pc[M]; bool pf[M];
+    lp1_all<M, I>(P, pv, radius, oi, true, pc, pf);
+    const bool viol = (I >= begin) && (I < n) && det(R.d[I], R.p[I] - result) > distance;
+    if (viol) {
+        V2 r2;
+        const int f = lp2_scan<M, I>(P, pv, I, pc, pf, mk(oi.x * radius, oi.y * radius), r2);
+        if (!(f < I)) result = r2;                 // failure keeps the current result (tempResult)
+        distance = det(R.d[I], R.p[I] - result);
+    }
+}
+
+// linearProgram3 (numObstLines == 0), speculative: per line the projected problem is built and solved branch-free.
+template <int M>
+__device__ __forceinline__ void lp3_spec(const RegLines<M> &R, int n, int begin, float radius, V2 &result)
+{
+    float distance = 0.0f;
+    // i == 0: no projected lines; linearProgram2 over an empty set returns optVelocity * radius
+    if (begin == 0 && n > 0 && det(R.d[0], R.p[0] - result) > 0.0f) {
+        result = mk(-R.d[0].y * radius, R.d[0].x * radius);
+        distance = det(R.d[0], R.p[0] - result);
+    }
+    if constexpr (M > 1) lp3_iter<M, 1>(R, n, begin, radius, result, distance);
+    if constexpr (M > 2) lp3_iter<M, 2>(R, n, begin, radius, result, distance);
+    if constexpr (M > 3) lp3_iter<M, 3>(R, n, begin, radius, result, distance);
+    if constexpr (M > 4) lp3_iter<M, 4>(R, n, begin, radius, result, distance);
+    static_assert(M <= 5, "lp3_spec is instantiated for at most 5 lines");
+}
+
+}  // namespace orca

@@ -17,126 +17,23 @@
 // per env. This kernel needs ~300 per env.
 #pragma once
 #include "crowdsim_common.cuh"
+#include "orca_spec.cuh"
 
 namespace cs {
 
 #define CS_FULL 0xffffffffu
 
-template <int M> struct RegLines { orca::V2 p[M], d[M]; };
-
-// linearProgram1 on register lines; lines 0..line_no-1 constrain line `line_no`. `n_prev` = line_no (template-unrolled).
-template <int M>
-__device__ __forceinline__ bool lp1_reg(const RegLines<M> &R, const bool (&valid)[M], int line_no, orca::V2 lp, orca::V2 ld,
-                                        float radius, orca::V2 opt, bool dir_opt, orca::V2 &result)
-{
-    using namespace orca;
-    const float dp = dot(lp, ld);
-    const float disc = sqr(dp) + sqr(radius) - abssq(lp);
-    if (disc < 0.0f) return false;
-    const float sq = sqrtf(disc);
-    float t_left = -dp - sq, t_right = -dp + sq;
-    #pragma unroll
-    for (int j = 0; j < M - 1; ++j) {
-        if (j < line_no && valid[j]) {
-            const float den = det(ld, R.d[j]);
-            const float num = det(R.d[j], lp - R.p[j]);
-            if (fabsf(den) <= kEps) {
-                if (num < 0.0f) return false;
-            } else {
-                const float t = num / den;
-                if (den >= 0.0f) t_right = (t < t_right) ? t : t_right;
-                else             t_left = (t_left < t) ? t : t_left;
-                if (t_left > t_right) return false;
-            }
-        }
-    }
-    if (dir_opt) {
-        if (dot(opt, ld) > 0.0f) result = lp + t_right * ld;
-        else                     result = lp + t_left * ld;
-    } else {
-        const float t = dot(ld, opt - lp);
-        if (t < t_left)       result = lp + t_left * ld;
-        else if (t > t_right) result = lp + t_right * ld;
-        else                  result = lp + t * ld;
-    }
-    return true;
-}
-
-// linearProgram2 over positions 0..count-1 (positions with valid[i] == false hold no line). Returns failing position or count.
-template <int M>
-__device__ __forceinline__ int lp2_reg(const RegLines<M> &R, const bool (&valid)[M], int count, float radius, orca::V2 opt,
-                                       bool dir_opt, orca::V2 &result)
-{
-    using namespace orca;
-    if (dir_opt)                          result = mk(opt.x * radius, opt.y * radius);
-    else if (abssq(opt) > sqr(radius)) { const V2 nv = normalize(opt); result = mk(nv.x * radius, nv.y * radius); }
-    else                                  result = opt;
-    #pragma unroll
-    for (int i = 0; i < M; ++i) {
-        if (i < count && valid[i]) {
-            if (det(R.d[i], R.p[i] - result) > 0.0f) {
-                const V2 tmp = result;
-                if (!lp1_reg<M>(R, valid, i, R.p[i], R.d[i], radius, opt, dir_opt, result)) { result = tmp; return i; }
-            }
-        }
-    }
-    return count;
-}
-
-// linearProgram3 (numObstLines == 0) on register lines.
-// Note on i == 0 in lp3: RVO2's loop starts at beginLine, which can be 0 (line 0 alone infeasible with the speed disc).
-// Then projLines is empty, lp2 over zero lines returns 0 == size (no failure) and sets result = optVelocity * radius
-// with optVelocity = (-dir.y, dir.x); handled explicitly in lp3_entry below.
-template <int M>
-__device__ __forceinline__ void lp3_entry(const RegLines<M> &R, int n, int begin, float radius, orca::V2 &result)
-{
-    using namespace orca;
-    float distance0 = 0.0f;
-    if (begin == 0 && n > 0) {
-        if (det(R.d[0], R.p[0] - result) > 0.0f) {
-            // empty projected-line set: linearProgram2 just returns its initial point
-            result = mk(-R.d[0].y * radius, R.d[0].x * radius);
-            distance0 = det(R.d[0], R.p[0] - result);
-        }
-    }
-    // continue with i >= 1, carrying `distance`
-    float distance = distance0;
-    #pragma unroll
-    for (int i = 1; i < M; ++i) {
-        if (i >= begin && i < n) {
-            if (det(R.d[i], R.p[i] - result) > distance) {
-                RegLines<M> P; bool pv[M];
-                #pragma unroll
-                for (int j = 0; j < M; ++j) { pv[j] = false; P.p[j] = mk(0.f, 0.f); P.d[j] = mk(0.f, 0.f); }
-                #pragma unroll
-                for (int j = 0; j < M - 1; ++j) {
-                    if (j < i) {
-                        const float d = det(R.d[i], R.d[j]);
-                        bool ok = true; V2 pp = mk(0.f, 0.f);
-                        if (fabsf(d) <= kEps) {
-                            if (dot(R.d[i], R.d[j]) > 0.0f) ok = false;
-                            else pp = 0.5f * (R.p[i] + R.p[j]);
-                        } else {
-                            const float t = det(R.d[j], R.p[i] - R.p[j]) / d;
-                            pp = R.p[i] + t * R.d[i];
-                        }
-                        if (ok) { pv[j] = true; P.p[j] = pp; P.d[j] = normalize(R.d[j] - R.d[i]); }
-                    }
-                }
-                const V2 tmp = result;
-                if (lp2_reg<M>(P, pv, i, radius, mk(-R.d[i].y, R.d[i].x), true, result) < i) result = tmp;
-                distance = det(R.d[i], R.p[i] - result);
-            }
-        }
-    }
-}
-
-template <int N>
+// EPW = whole envs packed per warp (1 .. 32/L). Dense packing (EPW = 32/L) minimises instructions per env-step and is
+// right when the batch fills the chip; sparse packing (fewer envs per warp, the other lanes idle) gives more,
+// less divergent warps and is faster when the batch is too small to hide latency (4096 envs = 0.8 dense warps per
+// SM sub-partition). COMPACT selects the block-compacted lp3 pass (pays two block barriers) over running lp3 in place.
+template <int N, int EPW, bool COMPACT>
 __global__ void __launch_bounds__(128) step_flat_kernel(const __grid_constant__ StepArgs A)
 {
     using namespace orca;
-    constexpr int L = N + 1, M = N, EPW = 32 / L, WPB = 4, T = 32 * WPB;
-    constexpr int QF = 4 * M + 5;                           // floats per queued lp3 work item
+    constexpr int L = N + 1, M = N, WPB = 4, T = 32 * WPB;
+    static_assert(EPW >= 1 && EPW * L <= 32, "envs per warp");
+    constexpr int QF = COMPACT ? 4 * M + 5 : 1;             // floats per queued lp3 work item
     __shared__ float s_q[QF][T];                            // [field][slot]: conflict-free for consecutive slots
     __shared__ float s_res[2][T];
     __shared__ int s_qcount;
@@ -149,7 +46,7 @@ __global__ void __launch_bounds__(128) step_flat_kernel(const __grid_constant__ 
     const bool is_robot = (a == N);
     bool live = (le < EPW) && (e < A.B);
     if (live && A.st.active) live = (A.st.active[e] != 0);
-    if (tid == 0) s_qcount = 0;
+    if (COMPACT && tid == 0) s_qcount = 0;
 
     // ---- own agent: coalesced 16-byte loads ----
     double2 pos = make_double2(0, 0), vel = pos, goal = pos, attr = make_double2(0.3, 1.0);
@@ -220,40 +117,46 @@ __global__ void __launch_bounds__(128) step_flat_kernel(const __grid_constant__ 
         const float rh = __shfl_sync(CS_FULL, frh, sl), rr = __shfl_sync(CS_FULL, frr, sl);
         valid[kk] = kk < nl;
         R.p[kk] = mk(0.f, 0.f); R.d[kk] = mk(0.f, 0.f);
-        if (valid[kk]) make_line(p, v, r, mk(qx, qy), mk(wx, wy), is_robot ? rr : rh, k.inv_time_horizon, k.inv_time_step, R.p[kk], R.d[kk]);
+        if (valid[kk]) make_line_sel(p, v, r, mk(qx, qy), mk(wx, wy), is_robot ? rr : rh, k.inv_time_horizon, k.inv_time_step, R.p[kk], R.d[kk]);
     }
 
     // ---- linear programs: lp2 in place, lp3 deferred to the block-compacted pass ----
+    // speculative lp1 candidates for every line (orca_spec.cuh), then linearProgram2 as a scan
+    V2 cand[M]; bool feas[M];
+    lp1_all<M, M>(R, valid, max_speed, pref, false, cand, feas);
     V2 nv = mk(0.f, 0.f);
-    int fail = 0;
-    if (solves) fail = lp2_reg<M>(R, valid, nl, max_speed, pref, false, nv);
+    const int fail = lp2_scan<M, M>(R, valid, nl, cand, feas, lp2_init(pref, max_speed), nv);
     const bool need3 = solves && fail < nl;
-    __syncthreads();                                         // s_qcount = 0 visible
-    int slot = -1;
-    if (need3) {
-        slot = atomicAdd(&s_qcount, 1);
-        #pragma unroll
-        for (int kk = 0; kk < M; ++kk) {
-            s_q[4 * kk + 0][slot] = R.p[kk].x; s_q[4 * kk + 1][slot] = R.p[kk].y;
-            s_q[4 * kk + 2][slot] = R.d[kk].x; s_q[4 * kk + 3][slot] = R.d[kk].y;
-        }
-        s_q[4 * M + 0][slot] = __int_as_float(nl); s_q[4 * M + 1][slot] = __int_as_float(fail);
-        s_q[4 * M + 2][slot] = max_speed; s_q[4 * M + 3][slot] = nv.x; s_q[4 * M + 4][slot] = nv.y;
-    }
-    if (__syncthreads_or(need3 ? 1 : 0)) {
-        const int cnt = s_qcount;
-        if (tid < cnt) {                                     // dense: work item q is handled by thread q
-            RegLines<M> Q;
+    if constexpr (!COMPACT) {
+        if (need3) lp3_spec<M>(R, nl, fail, max_speed, nv);
+    } else {
+        __syncthreads();                                     // s_qcount = 0 visible
+        int slot = -1;
+        if (need3) {
+            slot = atomicAdd(&s_qcount, 1);
             #pragma unroll
-            for (int kk = 0; kk < M; ++kk) { Q.p[kk] = mk(s_q[4 * kk + 0][tid], s_q[4 * kk + 1][tid]); Q.d[kk] = mk(s_q[4 * kk + 2][tid], s_q[4 * kk + 3][tid]); }
-            const int qn = __float_as_int(s_q[4 * M + 0][tid]), qf = __float_as_int(s_q[4 * M + 1][tid]);
-            const float qr = s_q[4 * M + 2][tid];
-            V2 res = mk(s_q[4 * M + 3][tid], s_q[4 * M + 4][tid]);
-            lp3_entry<M>(Q, qn, qf, qr, res);
-            s_res[0][tid] = res.x; s_res[1][tid] = res.y;
+            for (int kk = 0; kk < M; ++kk) {
+                s_q[4 * kk + 0][slot] = R.p[kk].x; s_q[4 * kk + 1][slot] = R.p[kk].y;
+                s_q[4 * kk + 2][slot] = R.d[kk].x; s_q[4 * kk + 3][slot] = R.d[kk].y;
+            }
+            s_q[4 * M + 0][slot] = __int_as_float(nl); s_q[4 * M + 1][slot] = __int_as_float(fail);
+            s_q[4 * M + 2][slot] = max_speed; s_q[4 * M + 3][slot] = nv.x; s_q[4 * M + 4][slot] = nv.y;
         }
-        __syncthreads();
-        if (need3) nv = mk(s_res[0][slot], s_res[1][slot]);
+        if (__syncthreads_or(need3 ? 1 : 0)) {
+            const int cnt = s_qcount;
+            if (tid < cnt) {                                 // dense: work item q is handled by thread q
+                RegLines<M> Q;
+                #pragma unroll
+                for (int kk = 0; kk < M; ++kk) { Q.p[kk] = mk(s_q[4 * kk + 0][tid], s_q[4 * kk + 1][tid]); Q.d[kk] = mk(s_q[4 * kk + 2][tid], s_q[4 * kk + 3][tid]); }
+                const int qn = __float_as_int(s_q[4 * M + 0][tid]), qf = __float_as_int(s_q[4 * M + 1][tid]);
+                const float qr = s_q[4 * M + 2][tid];
+                V2 res = mk(s_q[4 * M + 3][tid], s_q[4 * M + 4][tid]);
+                lp3_spec<M>(Q, qn, qf, qr, res);
+                s_res[0][tid] = res.x; s_res[1][tid] = res.y;
+            }
+            __syncthreads();
+            if (need3) nv = mk(s_res[0][slot], s_res[1][slot]);
+        }
     }
 
     // ---- robot velocity of this step, broadcast inside the env ----
