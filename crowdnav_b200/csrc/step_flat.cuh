@@ -27,9 +27,12 @@ namespace cs {
 // right when the batch fills the chip; sparse packing (fewer envs per warp, the other lanes idle) gives more,
 // less divergent warps and is faster when the batch is too small to hide latency (4096 envs = 0.8 dense warps per
 // SM sub-partition). COMPACT selects the block-compacted lp3 pass (pays two block barriers) over running lp3 in place.
-template <int N, int EPW, bool COMPACT>
+// STAGE is a profiling aid (scripts/latency_probe.cu instantiates cut-down variants to attribute latency); the library
+// only instantiates the full kernel (STAGE = 99).
+template <int N, int EPW, bool COMPACT, int STAGE = 99>
 __global__ void __launch_bounds__(128) step_flat_kernel(const __grid_constant__ StepArgs A)
 {
+    if constexpr (STAGE == 0) return;
     using namespace orca;
     constexpr int L = N + 1, M = N, WPB = 4, T = 32 * WPB;
     static_assert(EPW >= 1 && EPW * L <= 32, "envs per warp");
@@ -61,6 +64,11 @@ __global__ void __launch_bounds__(128) step_flat_kernel(const __grid_constant__ 
             if (k.robot_policy == CROWDSIM_ROBOT_EXTERNAL_ROT) theta = A.st.r_theta[e];
             if (k.robot_policy != CROWDSIM_ROBOT_ORCA) ext = ld2(A.io.action, e);
         }
+    }
+    if constexpr (STAGE == 1) {            // loads + stores only
+        if (live && !is_robot) { const size_t i = (size_t)e * N + a; st2(A.st.h_pos, i, pos); st2(A.st.h_vel, i, make_double2(vel.x + goal.x * 0, vel.y + attr.x * 0)); }
+        if (live && is_robot) { st2(A.st.r_pos, e, pos); A.st.g_time[e] = gtime + ext.x * 0 + theta * 0; }
+        return;
     }
     // float32 view of myself for the other lanes of my env (rvo2 boundary casts, orca.py:100-110)
     const float fpx = (float)pos.x, fpy = (float)pos.y, fvx = (float)vel.x, fvy = (float)vel.y;
@@ -121,11 +129,22 @@ __global__ void __launch_bounds__(128) step_flat_kernel(const __grid_constant__ 
     }
 
     // ---- linear programs: lp2 in place, lp3 deferred to the block-compacted pass ----
+    if constexpr (STAGE == 2) {            // + preferred velocity, neighbour scan, ORCA lines
+        float acc = pref.x + pref.y;
+        #pragma unroll
+        for (int kk = 0; kk < M; ++kk) acc += R.p[kk].x + R.p[kk].y + R.d[kk].x + R.d[kk].y;
+        if (live && !is_robot) { const size_t i = (size_t)e * N + a; st2(A.st.h_vel, i, make_double2(vel.x, vel.y + (double)acc * 0)); }
+        return;
+    }
     // speculative lp1 candidates for every line (orca_spec.cuh), then linearProgram2 as a scan
     V2 cand[M]; bool feas[M];
     lp1_all<M, M>(R, valid, max_speed, pref, false, cand, feas);
     V2 nv = mk(0.f, 0.f);
     const int fail = lp2_scan<M, M>(R, valid, nl, cand, feas, lp2_init(pref, max_speed), nv);
+    if constexpr (STAGE == 3) {            // + lp1 candidates and the lp2 scan
+        if (live && !is_robot) { const size_t i = (size_t)e * N + a; st2(A.st.h_vel, i, make_double2(vel.x + (double)nv.x * 0, vel.y + (double)(nv.y + fail) * 0)); }
+        return;
+    }
     const bool need3 = solves && fail < nl;
     if constexpr (!COMPACT) {
         if (need3) lp3_spec<M>(R, nl, fail, max_speed, nv);
@@ -159,6 +178,10 @@ __global__ void __launch_bounds__(128) step_flat_kernel(const __grid_constant__ 
         }
     }
 
+    if constexpr (STAGE == 4) {            // + lp3
+        if (live && !is_robot) { const size_t i = (size_t)e * N + a; st2(A.st.h_vel, i, make_double2(vel.x + (double)nv.x * 0, vel.y + (double)nv.y * 0)); }
+        return;
+    }
     // ---- robot velocity of this step, broadcast inside the env ----
     double ax = 0, ay = 0, rvx = 0, rvy = 0;
     if (is_robot) {
