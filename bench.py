@@ -202,43 +202,61 @@ def run_ours(args):
         env.episodes.ep_case.fill_(-1)
         # train-phase seeds (crowd_sim.py:272-273): distinct scenes for every env of every pool and rank
         env.seed_stride = world * pools * B
+        env.enable_autoreset(args.rule, seed_stride=env.seed_stride)
         env.reset_seeds(torch.arange(B, dtype=torch.int64) + 2000 + (rank * pools + p) * B, rule=args.rule, seed_stride=env.seed_stride)
+        env.prefetch()
         envs.append(env)
-
-    def step_pool(env):
-        env.step()                                                                        # 1 launch: fused step kernel
-        env.reset_seeds(mask=env.done, rule=args.rule, seed_stride=env.seed_stride)      # 1 launch: scenes of finished envs
+    torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # The whole timed region is ONE CUDA graph of K steps (2K kernel nodes, a single dependent chain on one stream):
+    # One bench step = the fused step kernel on the main stream (it also installs the prefetched next scene of every env
+    # whose episode just ended) + one scene-prefetch kernel for that batch on a side stream (off the critical path: it
+    # only has to finish before the same batch is stepped again). The whole timed region is ONE CUDA graph of K steps:
     # Python/ctypes launch overhead (~20 us per call) would otherwise dominate a 4096-env step.
-    side = torch.cuda.Stream(device=dev)
+    main = torch.cuda.Stream(device=dev)
+    sides = [torch.cuda.Stream(device=dev) for _ in range(4)]
     it = 0
-    with torch.cuda.stream(side):
-        for _ in range(3):
-            step_pool(envs[it % pools]); it += 1
-    torch.cuda.synchronize()
 
-    def capture(n_steps, fn):
+    def capture(n_steps, with_prefetch=True, step_fn=None):
         nonlocal it
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, stream=side):
+        pending = {}                                   # pool -> event of its last prefetch inside this capture
+        with torch.cuda.graph(g, stream=main):
             for _ in range(n_steps):
-                fn(envs[it % pools]); it += 1
+                p = it % pools; env = envs[p]; it += 1
+                if p in pending:
+                    main.wait_event(pending.pop(p))
+                (step_fn or (lambda e: e.step()))(env)
+                if with_prefetch:
+                    ev = torch.cuda.Event(); ev.record(main)
+                    sd = sides[p % len(sides)]
+                    sd.wait_event(ev)
+                    with torch.cuda.stream(sd):
+                        env.prefetch()
+                        done = torch.cuda.Event(); done.record(sd)
+                    pending[p] = done
+            for ev in pending.values():                # join the side branches
+                main.wait_event(ev)
         return g
-    g_warm = capture(max(W, 3), step_pool)
-    g_timed = capture(K, step_pool)
-    g_warm.replay()
+    with torch.cuda.stream(main):
+        for _ in range(3):
+            envs[it % pools].step(); envs[it % pools].prefetch(); it += 1
+    torch.cuda.synchronize()
+    g_warm = capture(max(W, 3))
+    g_timed = capture(K)
+    with torch.cuda.stream(main):
+        g_warm.replay()
     barrier()
     sampler = ClockSampler(local); sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    g_timed.replay()
-    e1.record()
+    with torch.cuda.stream(main):
+        e0.record()
+        g_timed.replay()
+        e1.record()
     barrier()
     launches = 2 * K
     ms = e0.elapsed_time(e1)
@@ -253,17 +271,22 @@ def run_ours(args):
     # replayed R times; CUDA events on the launching stream; per-launch duration = elapsed / (R * pools). The pools
     # rotate, so each launch reads its state from HBM, not L2. ----
     def step_only(env):
-        ep, env.episodes = env.episodes, None        # no episode bookkeeping -> finished envs keep stepping (same work)
+        ep, ar = env.episodes, env.autoreset         # no bookkeeping / auto-reset: finished envs keep stepping (same work)
+        env.episodes = None; env.autoreset = None
         env.step()
-        env.episodes = ep
-    g_step = capture(pools, step_only)
-    g_step.replay(); torch.cuda.synchronize()
+        env.episodes, env.autoreset = ep, ar
+    g_step = capture(pools, with_prefetch=False, step_fn=step_only)
+    with torch.cuda.stream(main):
+        g_step.replay()
+    torch.cuda.synchronize()
     R = max(3, min(20, 1200 // pools))
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record()
-    for _ in range(R):
-        g_step.replay()
-    k1.record(); torch.cuda.synchronize()
+    with torch.cuda.stream(main):
+        k0.record()
+        for _ in range(R):
+            g_step.replay()
+        k1.record()
+    torch.cuda.synchronize()
     k_avg = k0.elapsed_time(k1) / (R * pools)
     peak, peak_src = load_peaks()
     achieved = B * bytes_per_env / (k_avg * 1e-3) / 1e9
@@ -281,7 +304,7 @@ def run_ours(args):
     from crowdnav_b200.batched import HostStepper
     env = envs[0]
     env.set_robot_policy('external_xy')
-    stepper = HostStepper(env, auto_reset_rule=args.rule, seed_stride=env.seed_stride, next_orca_action=True)
+    stepper = HostStepper(env, next_orca_action=True)
     stepper.step()
     for _ in range(5):
         stepper.h_action.copy_(stepper.h_next_action); stepper.step()
@@ -297,7 +320,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * ke / float(t.item())
     h2d, d2h = stepper.h2d_bytes, stepper.d2h_bytes
-    launches_note = 'timed region: %d step + %d reset kernel launches (one CUDA graph)' % (K, K)
+    launches_note = 'timed region: %d step + %d scene-prefetch kernel launches (one CUDA graph, prefetch on side streams)' % (K, K)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -7,7 +7,7 @@ for its CPU library. No torch types cross the boundary.
 import ctypes as C
 import os
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_HUMANS = 63
 MAX_NEIGHBORS = 10
 
@@ -52,7 +52,17 @@ class ResetArgs(C.Structure):
                 ('circle_radius', C.c_double), ('square_width', C.c_double), ('human_radius', C.c_double),
                 ('human_v_pref', C.c_double), ('robot_radius', C.c_double), ('robot_v_pref', C.c_double),
                 ('discomfort_dist', C.c_double), ('randomize_attributes', C.c_int32),
-                ('mt_scratch', C.c_void_p)]
+                ('mt_scratch', C.c_void_p), ('case_counter', C.c_void_p), ('case_total', C.c_int32),
+                ('seed_base', C.c_uint32)]
+
+
+class AutoReset(C.Structure):
+    _fields_ = [('n_h_pos', C.c_void_p), ('n_h_goal', C.c_void_p), ('n_h_attr', C.c_void_p), ('n_case', C.c_void_p),
+                ('n_state', C.c_void_p), ('want', C.c_void_p), ('circle_radius', C.c_double),
+                ('robot_radius', C.c_double), ('robot_v_pref', C.c_double)]
+
+
+SLOT_EMPTY, SLOT_READY, SLOT_EXHAUSTED = 0, 1, 2
 
 
 def declare(lib, prefix='crowdsim_', with_stream=True):
@@ -60,7 +70,9 @@ def declare(lib, prefix='crowdsim_', with_stream=True):
     s = [C.c_void_p] if with_stream else []
     P = C.POINTER
     f = getattr(lib, prefix + 'step')
-    f.restype, f.argtypes = C.c_int, [P(Params), C.c_int, C.c_int, P(State), P(StepIO), P(Episodes)] + s
+    f.restype, f.argtypes = C.c_int, [P(Params), C.c_int, C.c_int, P(State), P(StepIO), P(Episodes), P(AutoReset)] + s
+    f = getattr(lib, prefix + 'prefetch_scenes')
+    f.restype, f.argtypes = C.c_int, [P(ResetArgs), C.c_int, C.c_int, P(AutoReset)] + s
     f = getattr(lib, prefix + 'orca_act')
     f.restype, f.argtypes = C.c_int, [P(Params), C.c_int, C.c_int, P(State), C.c_void_p] + s
     f = getattr(lib, prefix + 'reset')
@@ -74,7 +86,7 @@ def declare(lib, prefix='crowdsim_', with_stream=True):
 
 
 EXPORTS = ('crowdsim_abi_version', 'crowdsim_device_check', 'crowdsim_launch_count', 'crowdsim_debug_force_generic', 'crowdsim_debug_force_epw', 'crowdsim_step',
-           'crowdsim_orca_act', 'crowdsim_reset', 'crowdsim_pack_joint', 'crowdsim_lookahead_pack')
+           'crowdsim_orca_act', 'crowdsim_reset', 'crowdsim_prefetch_scenes', 'crowdsim_pack_joint', 'crowdsim_lookahead_pack')
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc', 'libcrowdsim_b200.so')
 _lib = None

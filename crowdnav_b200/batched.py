@@ -81,6 +81,31 @@ class EpisodeBuffers(object):
                              _ptr(self.res_too_close), _ptr(self.res_min_dist_sum), _ptr(self.res_final_rpos))
 
 
+class AutoResetBuffers(object):
+    """crowdsim_autoreset: one prefetched "next scene" slot per env (see include/crowdsim_b200.h)."""
+
+    def __init__(self, B, N, device, circle_radius, robot_radius, robot_v_pref):
+        f64 = lambda *s: torch.zeros(s, dtype=torch.float64, device=device)  # noqa: E731
+        self.n_h_pos, self.n_h_goal, self.n_h_attr = f64(B, N, 2), f64(B, N, 2), f64(B, N, 2)
+        self.n_case = torch.full((B,), -1, dtype=torch.int32, device=device)
+        self.n_state = torch.zeros(B, dtype=torch.uint8, device=device)
+        self.want = torch.zeros(B, dtype=torch.uint8, device=device)
+        self.circle_radius, self.robot_radius, self.robot_v_pref = circle_radius, robot_radius, robot_v_pref
+
+    FIELDS = ('n_h_pos', 'n_h_goal', 'n_h_attr', 'n_case', 'n_state', 'want')
+
+    def struct(self):
+        return _abi.AutoReset(_ptr(self.n_h_pos), _ptr(self.n_h_goal), _ptr(self.n_h_attr), _ptr(self.n_case),
+                              _ptr(self.n_state), _ptr(self.want), self.circle_radius, self.robot_radius, self.robot_v_pref)
+
+    def load_host(self, host):
+        for f in self.FIELDS:
+            getattr(self, f).copy_(torch.from_numpy(np.ascontiguousarray(getattr(host, f))))
+
+    def to_host(self):
+        return {f: getattr(self, f).cpu().numpy() for f in self.FIELDS}
+
+
 class BatchedCrowdSim(object):
     def __init__(self, num_envs, device='cuda:0'):
         self.lib = _abi.load()
@@ -102,8 +127,10 @@ class BatchedCrowdSim(object):
         self.human_safety_space = 0.0; self.robot_safety_space = 0.0
         # ORCA constants (orca.py:61-64)
         self.neighbor_dist = 10.0; self.max_neighbors = 10; self.time_horizon = 5.0
-        self.state = None; self.episodes = None
-        self._mt_scratch = None
+        self.state = None; self.episodes = None; self.autoreset = None
+        self._mt_scratch = None; self._mt_scratch_prefetch = None
+        self._case_counter = None; self._case_total = 0; self._seed_base = 0
+        self._ar_rule = None; self._ar_seed_stride = 0
 
     # ---- configuration -------------------------------------------------------------------------------------------
     def configure(self, config):
@@ -185,22 +212,51 @@ class BatchedCrowdSim(object):
         # uint32 bit patterns stored in an int32 tensor
         self._seed32.copy_(((seeds + 2 ** 31) % 2 ** 32 - 2 ** 31).to(torch.int32))
 
-    def reset_seeds(self, seeds=None, mask=None, rule='circle_crossing', seed_stride=0):
+    def _reset_args(self, mask, rule, seed_stride, scratch, use_queue):
+        q = use_queue and self._case_counter is not None
+        return _abi.ResetArgs(_ptr(mask), _ptr(self._seed32), int(seed_stride) % 2 ** 32, _abi.RULES[rule], self.circle_radius,
+                              self.square_width, self.human_radius, self.human_v_pref, self.robot_radius, self.robot_v_pref,
+                              self.discomfort_dist, int(bool(self.randomize_attributes)), _ptr(scratch),
+                              _ptr(self._case_counter) if q else None, self._case_total if q else 0, self._seed_base if q else 0)
+
+    def reset_seeds(self, seeds=None, mask=None, rule='circle_crossing', seed_stride=0, use_queue=False):
         """crowdsim_reset for the envs selected by `mask` (uint8 device tensor, None = all) from the per-slot seeds.
-        With seed_stride != 0 the slot's seed is advanced on device after use (auto-reset without host work)."""
+        With seed_stride != 0 the slot's seed is advanced on device after use; with use_queue the seeds come from the
+        shared case queue set up by set_case_queue()."""
         if seeds is not None:
             self.set_seeds(seeds)
         if mask is not None and not (isinstance(mask, torch.Tensor) and mask.dtype == torch.uint8 and mask.device == self.device):
             mask = torch.as_tensor(mask).to(device=self.device, dtype=torch.uint8)
-        a = _abi.ResetArgs(_ptr(mask), _ptr(self._seed32), int(seed_stride) % 2 ** 32, _abi.RULES[rule], self.circle_radius,
-                           self.square_width, self.human_radius, self.human_v_pref, self.robot_radius, self.robot_v_pref,
-                           self.discomfort_dist, int(bool(self.randomize_attributes)), _ptr(self._mt_scratch))
+        a = self._reset_args(mask, rule, seed_stride, self._mt_scratch, use_queue)
         st = self.state.struct()
         ep = self.episodes.struct() if self.episodes is not None else None
         rc = self.lib.crowdsim_reset(C.byref(a), self.B, self.human_num, C.byref(st),
                                      C.byref(ep) if ep is not None else None, self._stream())
         _abi.check(rc, 'crowdsim_reset')
         self._keep = (mask, a)
+
+    # ---- auto-reset with prefetched scenes -------------------------------------------------------------------------
+    def set_case_queue(self, first_case, total, phase='test'):
+        """Shared work queue of `total` cases starting at `first_case` of `phase` (seed = offset[phase] + case):
+        env slots pull the next case on device when their episode ends (Explorer.run_k_episodes with k > slots)."""
+        self._case_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._case_total = int(total)
+        self._seed_base = (_PHASE_OFFSET[phase] + int(first_case)) % 2 ** 32
+
+    def enable_autoreset(self, rule='circle_crossing', seed_stride=0):
+        """Allocate the per-slot next-scene buffers; step() then re-initialises finished envs in the same launch.
+        Call prefetch() (any stream) to (re)fill consumed slots."""
+        self.autoreset = AutoResetBuffers(self.B, self.human_num, self.device, self.circle_radius, self.robot_radius,
+                                          self.robot_v_pref)
+        self._mt_scratch_prefetch = torch.empty((624, self.B), dtype=torch.int32, device=self.device)
+        self._ar_rule, self._ar_seed_stride = rule, seed_stride
+        return self.autoreset
+
+    def prefetch(self):
+        a = self._reset_args(None, self._ar_rule, self._ar_seed_stride, self._mt_scratch_prefetch, True)
+        ar = self.autoreset.struct()
+        rc = self.lib.crowdsim_prefetch_scenes(C.byref(a), self.B, self.human_num, C.byref(ar), self._stream())
+        _abi.check(rc, 'crowdsim_prefetch_scenes')
 
     # ---- step ----------------------------------------------------------------------------------------------------
     def step(self, actions=None):
@@ -215,8 +271,10 @@ class BatchedCrowdSim(object):
         io = _abi.StepIO(_ptr(self.action), _ptr(self.action_out), _ptr(self.reward), _ptr(self.dmin),
                          _ptr(self.done), _ptr(self.info))
         ep = self.episodes.struct() if self.episodes is not None else None
+        ar = self.autoreset.struct() if self.autoreset is not None else None
         rc = self.lib.crowdsim_step(C.byref(prm), self.B, self.human_num, C.byref(st), C.byref(io),
-                                    C.byref(ep) if ep is not None else None, self._stream())
+                                    C.byref(ep) if ep is not None else None, C.byref(ar) if ar is not None else None,
+                                    self._stream())
         _abi.check(rc, 'crowdsim_step')
         return self.observation(), self.reward, self.done, self.info
 
@@ -260,12 +318,12 @@ class HostStepper(object):
     action to env.step and gets observation, reward, done, info back -- crowd_nav/utils/explorer.py:42-43).
 
     One call = one CUDA graph replay: H2D copy of the robot actions from pinned memory, the fused step kernel,
-    on-device regeneration of finished envs' scenes (optional), the robot's next ORCA decision (optional, so a host
+    refill of the consumed next-scene slots (when env.enable_autoreset() was called), the robot's next ORCA decision (optional, so a host
     loop can drive an ORCA robot), D2H copies of everything a caller reads, then a stream synchronise.
     Buffers: self.h_action [B][2] (write before step()); results in self.h_pos, h_vel [B][N][2], h_reward, h_done,
     h_info [B], h_next_action [B][2] (pinned torch tensors; .numpy() views are free)."""
 
-    def __init__(self, env, auto_reset_rule=None, seed_stride=0, next_orca_action=True):
+    def __init__(self, env, next_orca_action=True):
         self.env = env
         B, N, dev = env.B, env.human_num, env.device
         pin = lambda *shape, dtype=torch.float64: torch.zeros(shape, dtype=dtype).pin_memory()  # noqa: E731
@@ -280,13 +338,13 @@ class HostStepper(object):
         self.d2h_bytes = sum(t.numel() * t.element_size() for t in (self.h_pos, self.h_vel, self.h_reward, self.h_done, self.h_info))
         if next_orca_action:
             self.d2h_bytes += self.h_next_action.numel() * 8
-        self.kernels_per_step = 1 + (1 if auto_reset_rule else 0) + (1 if next_orca_action else 0)
+        self.kernels_per_step = 1 + (1 if env.autoreset is not None else 0) + (1 if next_orca_action else 0)
 
         def body():
             self.d_action.copy_(self.h_action, non_blocking=True)
-            env.step(self.d_action)
-            if auto_reset_rule:
-                env.reset_seeds(mask=env.done, rule=auto_reset_rule, seed_stride=seed_stride)
+            env.step(self.d_action)                    # installs prefetched scenes of finished envs when auto-reset is on
+            if env.autoreset is not None:
+                env.prefetch()
             if next_orca_action:
                 env.orca_act(self.d_next)
                 self.h_next_action.copy_(self.d_next, non_blocking=True)

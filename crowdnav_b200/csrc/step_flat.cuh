@@ -196,16 +196,13 @@ __global__ void __launch_bounds__(128) step_flat_kernel(const __grid_constant__ 
 
     // ---- human lanes: swept-segment clearance (crowd_sim.py:333-345) + Euler step (agent.py:122-135) ----
     const double dt = k.time_step;
+    const bool env_ok = (le < EPW) && (e < A.B);
     double closest = 0.0;
     if (live && !is_robot) {
         const double px = pos.x - Rpx, py = pos.y - Rpy;
         const double vx = vel.x - Rvx, vy = vel.y - Rvy;
         const double ex = px + vx * dt, ey = py + vy * dt;
         closest = point_to_segment_dist0(px, py, ex, ey) - attr.x - Rrad;
-        const double hx = (double)nv.x, hy = (double)nv.y;
-        const size_t i = (size_t)e * N + a;
-        st2(A.st.h_pos, i, make_double2(pos.x + hx * dt, pos.y + hy * dt));
-        st2(A.st.h_vel, i, make_double2(hx, hy));
     }
     // ordered fold over the env's humans (first collision breaks, crowd_sim.py:346-351); consumed by the robot lane
     double dmin = __longlong_as_double(0x7ff0000000000000LL); bool collision = false;
@@ -214,47 +211,65 @@ __global__ void __launch_bounds__(128) step_flat_kernel(const __grid_constant__ 
         const double ci = __shfl_sync(CS_FULL, closest, ebase + i);
         if (!collision) { if (ci < 0) collision = true; else if (ci < dmin) dmin = ci; }
     }
-    if (!live || !is_robot) return;
 
-    // ---- robot lane: ladder, update, bookkeeping ----
-    double npx, npy, nvx, nvy;
-    if (k.robot_policy != CROWDSIM_ROBOT_EXTERNAL_ROT) { npx = pos.x + ax * dt; npy = pos.y + ay * dt; nvx = ax; nvy = ay; }
-    else { const double th = theta + ay; npx = pos.x + cos(th) * ax * dt; npy = pos.y + sin(th) * ax * dt; nvx = nvy = 0; }
-    const bool reaching_goal = norm2(npx - goal.x, npy - goal.y) < attr.x;
-    double reward; bool done; int info;
-    if (gtime >= k.time_limit - 1) { reward = 0; done = true; info = CROWDSIM_INFO_TIMEOUT; }
-    else if (collision) { reward = k.collision_penalty; done = true; info = CROWDSIM_INFO_COLLISION; }
-    else if (reaching_goal) { reward = k.success_reward; done = true; info = CROWDSIM_INFO_REACHGOAL; }
-    else if (dmin < k.discomfort_dist) { reward = (dmin - k.discomfort_dist) * k.discomfort_penalty_factor * dt; done = false; info = CROWDSIM_INFO_DANGER; }
-    else { reward = 0; done = false; info = CROWDSIM_INFO_NOTHING; }
-    if (k.robot_policy == CROWDSIM_ROBOT_EXTERNAL_ROT) {
-        double nth = fmod(theta + ay, 2 * CS_PI); if (nth < 0) nth += 2 * CS_PI;
-        A.st.r_theta[e] = nth; nvx = ax * cos(nth); nvy = ax * sin(nth);
-    }
-    st2(A.st.r_pos, e, make_double2(npx, npy));
-    st2(A.st.r_vel, e, make_double2(nvx, nvy));
-    const double ntime = gtime + dt;
-    A.st.g_time[e] = ntime;
-    if (A.io.action_out) st2(A.io.action_out, e, make_double2(nvx, nvy));
-    A.io.reward[e] = reward; A.io.dmin[e] = dmin; A.io.done[e] = done ? 1 : 0; A.io.info[e] = (uint8_t)info;
-    if (A.has_ep) {
-        const crowdsim_episodes &ep = A.ep;
-        const int t = ep.ep_steps[e];
-        const double disc = (t < ep.discount_len) ? ep.discount[t] : 0.0;
-        const double ret = ep.ep_return[e] + disc * reward;
-        int tc = ep.ep_too_close[e]; double mds = ep.ep_min_dist_sum[e];
-        if (info == CROWDSIM_INFO_DANGER) { tc += 1; mds += dmin; ep.ep_too_close[e] = tc; ep.ep_min_dist_sum[e] = mds; }
-        ep.ep_return[e] = ret; ep.ep_steps[e] = t + 1;
-        if (done) {
-            const int cs_ = ep.ep_case[e];
-            if (cs_ >= 0) {
-                ep.res_info[cs_] = (uint8_t)info; ep.res_steps[cs_] = t + 1;
-                ep.res_time[cs_] = (info == CROWDSIM_INFO_TIMEOUT) ? k.time_limit : ntime;
-                ep.res_return[cs_] = ret; ep.res_too_close[cs_] = tc; ep.res_min_dist_sum[cs_] = mds;
-                if (ep.res_final_rpos) st2(ep.res_final_rpos, cs_, make_double2(npx, npy));
+    // ---- robot lane: ladder, update, bookkeeping; decides about auto-reset ----
+    int install = 0;
+    if (is_robot && env_ok) {
+        bool done = false;
+        if (live) {
+            double npx, npy, nvx, nvy;
+            if (k.robot_policy != CROWDSIM_ROBOT_EXTERNAL_ROT) { npx = pos.x + ax * dt; npy = pos.y + ay * dt; nvx = ax; nvy = ay; }
+            else { const double th = theta + ay; npx = pos.x + cos(th) * ax * dt; npy = pos.y + sin(th) * ax * dt; nvx = nvy = 0; }
+            const bool reaching_goal = norm2(npx - goal.x, npy - goal.y) < attr.x;
+            double reward; int info;
+            if (gtime >= k.time_limit - 1) { reward = 0; done = true; info = CROWDSIM_INFO_TIMEOUT; }
+            else if (collision) { reward = k.collision_penalty; done = true; info = CROWDSIM_INFO_COLLISION; }
+            else if (reaching_goal) { reward = k.success_reward; done = true; info = CROWDSIM_INFO_REACHGOAL; }
+            else if (dmin < k.discomfort_dist) { reward = (dmin - k.discomfort_dist) * k.discomfort_penalty_factor * dt; done = false; info = CROWDSIM_INFO_DANGER; }
+            else { reward = 0; done = false; info = CROWDSIM_INFO_NOTHING; }
+            if (k.robot_policy == CROWDSIM_ROBOT_EXTERNAL_ROT) {
+                double nth = fmod(theta + ay, 2 * CS_PI); if (nth < 0) nth += 2 * CS_PI;
+                A.st.r_theta[e] = nth; nvx = ax * cos(nth); nvy = ax * sin(nth);
             }
-            if (A.st.active) A.st.active[e] = 0;
+            st2(A.st.r_pos, e, make_double2(npx, npy));
+            st2(A.st.r_vel, e, make_double2(nvx, nvy));
+            const double ntime = gtime + dt;
+            A.st.g_time[e] = ntime;
+            if (A.io.action_out) st2(A.io.action_out, e, make_double2(nvx, nvy));
+            A.io.reward[e] = reward; A.io.dmin[e] = dmin; A.io.done[e] = done ? 1 : 0; A.io.info[e] = (uint8_t)info;
+            if (A.has_ep) {
+                const crowdsim_episodes &ep = A.ep;
+                const int t = ep.ep_steps[e];
+                const double disc = (t < ep.discount_len) ? ep.discount[t] : 0.0;
+                const double ret = ep.ep_return[e] + disc * reward;
+                int tc = ep.ep_too_close[e]; double mds = ep.ep_min_dist_sum[e];
+                if (info == CROWDSIM_INFO_DANGER) { tc += 1; mds += dmin; ep.ep_too_close[e] = tc; ep.ep_min_dist_sum[e] = mds; }
+                ep.ep_return[e] = ret; ep.ep_steps[e] = t + 1;
+                if (done) {
+                    const int cs_ = ep.ep_case[e];
+                    if (cs_ >= 0) {
+                        ep.res_info[cs_] = (uint8_t)info; ep.res_steps[cs_] = t + 1;
+                        ep.res_time[cs_] = (info == CROWDSIM_INFO_TIMEOUT) ? k.time_limit : ntime;
+                        ep.res_return[cs_] = ret; ep.res_too_close[cs_] = tc; ep.res_min_dist_sum[cs_] = mds;
+                        if (ep.res_final_rpos) st2(ep.res_final_rpos, cs_, make_double2(npx, npy));
+                    }
+                    if (A.st.active && !A.has_ar) A.st.active[e] = 0;
+                }
+            }
         }
+        if (A.has_ar) install = ar_decide(A, e, live && done, !live && A.ar.want[e] != 0);
+    }
+    if (A.has_ar) {                                          // warp-uniform
+        install = __shfl_sync(CS_FULL, install, rl) && env_ok;
+        if (install) { if (is_robot) ar_install_robot(A, e); else ar_install_human(A, e, N, a); }
+        __syncwarp();
+        if (install && is_robot) *reinterpret_cast<volatile uint8_t *>(A.ar.n_state + e) = CROWDSIM_SLOT_EMPTY;
+    }
+    if (live && !is_robot && !install) {
+        const double hx = (double)nv.x, hy = (double)nv.y;
+        const size_t i = (size_t)e * N + a;
+        st2(A.st.h_pos, i, make_double2(pos.x + hx * dt, pos.y + hy * dt));
+        st2(A.st.h_vel, i, make_double2(hx, hy));
     }
 }
 

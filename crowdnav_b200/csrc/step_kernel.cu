@@ -26,9 +26,44 @@ struct StepArgs {
     crowdsim_state st;
     crowdsim_step_io io;
     crowdsim_episodes ep;
-    int has_ep;
+    crowdsim_autoreset ar;
+    int has_ep, has_ar;
     int act_only;      // crowdsim_orca_act: robot lanes solve and write action_out, nothing is mutated
 };
+
+// ---- auto-reset protocol, consumer side (include/crowdsim_b200.h: crowdsim_autoreset) ----
+// Robot lane: an env that just finished (or is parked waiting) looks at its next-scene slot. Returns 1 = install now.
+__device__ __forceinline__ int ar_decide(const StepArgs &A, int e, bool finished, bool parked)
+{
+    if (!(finished || parked)) return 0;
+    const uint8_t s = *reinterpret_cast<volatile uint8_t *>(A.ar.n_state + e);
+    if (s == CROWDSIM_SLOT_READY) return 1;
+    A.st.active[e] = 0;                                        // park: nothing to install (yet)
+    A.ar.want[e] = (s == CROWDSIM_SLOT_EXHAUSTED) ? 0 : 1;
+    return 0;
+}
+// Human lane a of env e: copy the prefetched scene into the live state (agent.py:47-58 set(px,py,gx,gy,0,0,...)).
+__device__ __forceinline__ void ar_install_human(const StepArgs &A, int e, int N, int a)
+{
+    __threadfence();                                           // the slot was published with a fence; read after the flag
+    const size_t i = (size_t)e * N + a;
+    st2(A.st.h_pos, i, ld2(A.ar.n_h_pos, i)); st2(A.st.h_vel, i, make_double2(0, 0));
+    st2(A.st.h_goal, i, ld2(A.ar.n_h_goal, i)); st2(A.st.h_attr, i, ld2(A.ar.n_h_attr, i));
+}
+// Robot lane of env e: crowd_sim.py:262,274 (global_time = 0, robot.set(0,-R,0,R,0,0,pi/2)) + fresh episode accumulators.
+__device__ __forceinline__ void ar_install_robot(const StepArgs &A, int e)
+{
+    __threadfence();
+    st2(A.st.r_pos, e, make_double2(0.0, -A.ar.circle_radius)); st2(A.st.r_goal, e, make_double2(0.0, A.ar.circle_radius));
+    st2(A.st.r_vel, e, make_double2(0, 0)); st2(A.st.r_attr, e, make_double2(A.ar.robot_radius, A.ar.robot_v_pref));
+    if (A.st.r_theta) A.st.r_theta[e] = CS_PI / 2;
+    A.st.g_time[e] = 0.0;
+    if (A.has_ep) {
+        A.ep.ep_steps[e] = 0; A.ep.ep_return[e] = 0.0; A.ep.ep_too_close[e] = 0; A.ep.ep_min_dist_sum[e] = 0.0;
+        A.ep.ep_case[e] = A.ar.n_case[e];
+    }
+    A.st.active[e] = 1; A.ar.want[e] = 0;
+}
 
 }  // namespace cs
 #include "step_flat.cuh"
@@ -99,64 +134,77 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepA
     }
     __syncthreads();
 
-    if (!live) return;
-    if (!is_robot) {
+    // ---- robot lane: reduce clearances, ladder, update, bookkeeping; decides about auto-reset ----
+    const bool env_ok = (e < A.B);
+    int install = 0;
+    if (is_robot && env_ok) {
+        bool done = false;
+        if (live) {
+            double dmin = __longlong_as_double(0x7ff0000000000000LL); bool collision = false;
+            for (int i = 0; i < N; ++i) {           // crowd_sim.py:346-351 (first collision breaks; dmin only matters without one)
+                const double c = s.closest[le * L + i];
+                if (c < 0) { collision = true; break; }
+                else if (c < dmin) dmin = c;
+            }
+            double npx, npy, nvx, nvy;
+            if (k.robot_policy != CROWDSIM_ROBOT_EXTERNAL_ROT) { npx = pos.x + ax * dt; npy = pos.y + ay * dt; nvx = ax; nvy = ay; }
+            else { const double th = theta + ay; npx = pos.x + cos(th) * ax * dt; npy = pos.y + sin(th) * ax * dt; nvx = nvy = 0; }  // agent.py:115-118
+            const bool reaching_goal = norm2(npx - goal.x, npy - goal.y) < attr.x;      // crowd_sim.py:365-366
+
+            double reward; int info;                                                   // crowd_sim.py:368-389
+            if (gtime >= k.time_limit - 1) { reward = 0; done = true; info = CROWDSIM_INFO_TIMEOUT; }
+            else if (collision) { reward = k.collision_penalty; done = true; info = CROWDSIM_INFO_COLLISION; }
+            else if (reaching_goal) { reward = k.success_reward; done = true; info = CROWDSIM_INFO_REACHGOAL; }
+            else if (dmin < k.discomfort_dist) { reward = (dmin - k.discomfort_dist) * k.discomfort_penalty_factor * dt; done = false; info = CROWDSIM_INFO_DANGER; }
+            else { reward = 0; done = false; info = CROWDSIM_INFO_NOTHING; }
+
+            if (k.robot_policy == CROWDSIM_ROBOT_EXTERNAL_ROT) {                        // agent.py:133-135
+                double nth = fmod(theta + ay, 2 * CS_PI); if (nth < 0) nth += 2 * CS_PI;
+                A.st.r_theta[e] = nth; nvx = ax * cos(nth); nvy = ax * sin(nth);
+            }
+            st2(A.st.r_pos, e, make_double2(npx, npy));
+            st2(A.st.r_vel, e, make_double2(nvx, nvy));
+            const double ntime = gtime + dt;
+            A.st.g_time[e] = ntime;
+            if (A.io.action_out) st2(A.io.action_out, e, make_double2(nvx, nvy));
+            A.io.reward[e] = reward; A.io.dmin[e] = dmin; A.io.done[e] = done ? 1 : 0; A.io.info[e] = (uint8_t)info;
+
+            if (A.has_ep) {                                                            // explorer.py:41-72
+                const crowdsim_episodes &ep = A.ep;
+                const int t = ep.ep_steps[e];
+                const double disc = (t < ep.discount_len) ? ep.discount[t] : 0.0;
+                const double ret = ep.ep_return[e] + disc * reward;
+                int tc = ep.ep_too_close[e]; double mds = ep.ep_min_dist_sum[e];
+                if (info == CROWDSIM_INFO_DANGER) { tc += 1; mds += dmin; ep.ep_too_close[e] = tc; ep.ep_min_dist_sum[e] = mds; }
+                ep.ep_return[e] = ret; ep.ep_steps[e] = t + 1;
+                if (done) {
+                    const int c = ep.ep_case[e];
+                    if (c >= 0) {
+                        ep.res_info[c] = (uint8_t)info; ep.res_steps[c] = t + 1;
+                        ep.res_time[c] = (info == CROWDSIM_INFO_TIMEOUT) ? k.time_limit : ntime;
+                        ep.res_return[c] = ret; ep.res_too_close[c] = tc; ep.res_min_dist_sum[c] = mds;
+                        if (ep.res_final_rpos) st2(ep.res_final_rpos, c, make_double2(npx, npy));
+                    }
+                    if (A.st.active && !A.has_ar) A.st.active[e] = 0;
+                }
+            }
+        }
+        if (A.has_ar) install = ar_decide(A, e, live && done, !live && A.ar.want[e] != 0);
+    }
+    if (A.has_ar) {
+        if (is_robot) s.closest[le * L + N] = (double)install;     // the robot's own clearance slot is unused: env-wide flag
+        __syncthreads();
+        install = (s.closest[le * L + N] != 0.0) && env_ok;
+        if (install) { if (is_robot) ar_install_robot(A, e); else ar_install_human(A, e, N, a); }
+        __syncthreads();
+        if (install && is_robot) *reinterpret_cast<volatile uint8_t *>(A.ar.n_state + e) = CROWDSIM_SLOT_EMPTY;
+    }
+    if (live && !is_robot && !install) {
         // agent.py:122-135 holonomic step with the ORCA action (float32 values widened)
         const double hx = (double)nv.x, hy = (double)nv.y;
         const size_t i = (size_t)e * N + a;
         st2(A.st.h_pos, i, make_double2(pos.x + hx * dt, pos.y + hy * dt));
         st2(A.st.h_vel, i, make_double2(hx, hy));
-        return;
-    }
-
-    // ---- robot lane: reduce clearances, ladder, update, bookkeeping ----
-    double dmin = __longlong_as_double(0x7ff0000000000000LL); bool collision = false;
-    for (int i = 0; i < N; ++i) {           // crowd_sim.py:346-351 (first collision breaks; dmin only matters without one)
-        const double c = s.closest[le * L + i];
-        if (c < 0) { collision = true; break; }
-        else if (c < dmin) dmin = c;
-    }
-    double npx, npy, nvx, nvy;
-    if (k.robot_policy != CROWDSIM_ROBOT_EXTERNAL_ROT) { npx = pos.x + ax * dt; npy = pos.y + ay * dt; nvx = ax; nvy = ay; }
-    else { const double th = theta + ay; npx = pos.x + cos(th) * ax * dt; npy = pos.y + sin(th) * ax * dt; nvx = nvy = 0; }  // agent.py:115-118
-    const bool reaching_goal = norm2(npx - goal.x, npy - goal.y) < attr.x;      // crowd_sim.py:365-366
-
-    double reward; bool done; int info;                                        // crowd_sim.py:368-389
-    if (gtime >= k.time_limit - 1) { reward = 0; done = true; info = CROWDSIM_INFO_TIMEOUT; }
-    else if (collision) { reward = k.collision_penalty; done = true; info = CROWDSIM_INFO_COLLISION; }
-    else if (reaching_goal) { reward = k.success_reward; done = true; info = CROWDSIM_INFO_REACHGOAL; }
-    else if (dmin < k.discomfort_dist) { reward = (dmin - k.discomfort_dist) * k.discomfort_penalty_factor * dt; done = false; info = CROWDSIM_INFO_DANGER; }
-    else { reward = 0; done = false; info = CROWDSIM_INFO_NOTHING; }
-
-    if (k.robot_policy == CROWDSIM_ROBOT_EXTERNAL_ROT) {                        // agent.py:133-135
-        double nth = fmod(theta + ay, 2 * CS_PI); if (nth < 0) nth += 2 * CS_PI;
-        A.st.r_theta[e] = nth; nvx = ax * cos(nth); nvy = ax * sin(nth);
-    }
-    st2(A.st.r_pos, e, make_double2(npx, npy));
-    st2(A.st.r_vel, e, make_double2(nvx, nvy));
-    const double ntime = gtime + dt;
-    A.st.g_time[e] = ntime;
-    if (A.io.action_out) st2(A.io.action_out, e, make_double2(nvx, nvy));
-    A.io.reward[e] = reward; A.io.dmin[e] = dmin; A.io.done[e] = done ? 1 : 0; A.io.info[e] = (uint8_t)info;
-
-    if (A.has_ep) {                                                            // explorer.py:41-72
-        const crowdsim_episodes &ep = A.ep;
-        const int t = ep.ep_steps[e];
-        const double disc = (t < ep.discount_len) ? ep.discount[t] : 0.0;
-        const double ret = ep.ep_return[e] + disc * reward;
-        int tc = ep.ep_too_close[e]; double mds = ep.ep_min_dist_sum[e];
-        if (info == CROWDSIM_INFO_DANGER) { tc += 1; mds += dmin; ep.ep_too_close[e] = tc; ep.ep_min_dist_sum[e] = mds; }
-        ep.ep_return[e] = ret; ep.ep_steps[e] = t + 1;
-        if (done) {
-            const int c = ep.ep_case[e];
-            if (c >= 0) {
-                ep.res_info[c] = (uint8_t)info; ep.res_steps[c] = t + 1;
-                ep.res_time[c] = (info == CROWDSIM_INFO_TIMEOUT) ? k.time_limit : ntime;
-                ep.res_return[c] = ret; ep.res_too_close[c] = tc; ep.res_min_dist_sum[c] = mds;
-                if (ep.res_final_rpos) st2(ep.res_final_rpos, c, make_double2(npx, npy));
-            }
-            if (A.st.active) A.st.active[e] = 0;
-        }
     }
 }
 
@@ -183,7 +231,7 @@ static int flat_pick_epw(int B, int N)
 }
 
 static int launch(const crowdsim_params *prm, int B, int N, const crowdsim_state *st, const crowdsim_step_io *io,
-                  const crowdsim_episodes *ep, int act_only, cudaStream_t stream)
+                  const crowdsim_episodes *ep, const crowdsim_autoreset *ar, int act_only, cudaStream_t stream)
 {
     if (!prm || !st || !io || B < 0 || N < 0) return CROWDSIM_EINVAL;
     if (N > CROWDSIM_MAX_HUMANS || prm->max_neighbors > CROWDSIM_MAX_NEIGHBORS) return CROWDSIM_EUNSUPPORTED;
@@ -198,6 +246,9 @@ static int launch(const crowdsim_params *prm, int B, int N, const crowdsim_state
     if (ep && !act_only && (!ep->ep_case || !ep->ep_steps || !ep->ep_return || !ep->ep_too_close || !ep->ep_min_dist_sum ||
                             !ep->discount || !ep->res_info || !ep->res_steps || !ep->res_time || !ep->res_return ||
                             !ep->res_too_close || !ep->res_min_dist_sum)) return CROWDSIM_EINVAL;
+    if (ar && !act_only) {
+        if (!st->active || !ar->n_state || !ar->n_case || !ar->want || (N > 0 && (!ar->n_h_pos || !ar->n_h_goal || !ar->n_h_attr))) return CROWDSIM_EINVAL;
+    }
     if (B == 0) return CROWDSIM_OK;
     StepArgs A;
     A.k = make_kparams(prm, N);
@@ -205,6 +256,8 @@ static int launch(const crowdsim_params *prm, int B, int N, const crowdsim_state
     A.B = B; A.N = N; A.L = N + 1; A.EPB = envs_per_block(A.L, 128);
     A.st = *st; A.io = *io; A.has_ep = (ep != nullptr && !act_only); A.act_only = act_only;
     if (A.has_ep) A.ep = *ep; else memset(&A.ep, 0, sizeof(A.ep));
+    A.has_ar = (ar != nullptr && !act_only);
+    if (A.has_ar) A.ar = *ar; else memset(&A.ar, 0, sizeof(A.ar));
     if (!act_only && N >= 1 && N <= 5 && !g_force_generic) {
         // small crowds: register-resident solver, whole envs per warp (step_flat.cuh). Packing: dense when the batch
         // fills the chip, sparse (fewer envs per warp, in-place lp3) when it does not -- see flat_pick_epw().
@@ -239,16 +292,16 @@ static int launch(const crowdsim_params *prm, int B, int N, const crowdsim_state
 }  // namespace cs
 
 extern "C" int crowdsim_step(const crowdsim_params *prm, int B, int N, crowdsim_state *st, crowdsim_step_io *io,
-                             crowdsim_episodes *ep, void *stream)
+                             crowdsim_episodes *ep, const crowdsim_autoreset *ar, void *stream)
 {
-    return cs::launch(prm, B, N, st, io, ep, 0, (cudaStream_t)stream);
+    return cs::launch(prm, B, N, st, io, ep, ar, 0, (cudaStream_t)stream);
 }
 
 extern "C" int crowdsim_orca_act(const crowdsim_params *prm, int B, int N, const crowdsim_state *st, double *action_out,
                                  void *stream)
 {
     crowdsim_step_io io; memset(&io, 0, sizeof(io)); io.action_out = action_out;
-    return cs::launch(prm, B, N, st, &io, nullptr, 1, (cudaStream_t)stream);
+    return cs::launch(prm, B, N, st, &io, nullptr, nullptr, 1, (cudaStream_t)stream);
 }
 
 extern "C" void crowdsim_debug_force_generic(int on) { cs::g_force_generic = on; }

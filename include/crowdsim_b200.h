@@ -15,6 +15,8 @@
  *                            per-step part of Explorer.run_k_episodes (explorer.py:41-72)
  *   crowdsim_orca_act        crowd_sim/envs/utils/robot.py:9-14 with policy ORCA (orca.py:82-132), batched
  *   crowdsim_reset           crowd_sim/envs/crowd_sim.py:251-312 + generators :155-207 (np.random MT19937)
+ *   crowdsim_prefetch_scenes the same generators, run ahead of time for the NEXT episode of each env slot
+ *                            (explorer.py:35-36: reset() of the following episode)
  *   crowdsim_lookahead_pack  crowd_nav/policy/multi_human_rl.py:35-45 = 81 x env.onestep_lookahead
  *                            (crowd_sim.py:314-315,414-416) + CADRL.propagate (cadrl.py:104-129) +
  *                            CADRL.rotate (cadrl.py:187-222), fused
@@ -33,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CROWDSIM_ABI_VERSION 1
+#define CROWDSIM_ABI_VERSION 2
 
 /* error codes */
 #define CROWDSIM_OK            0
@@ -127,7 +129,31 @@ typedef struct crowdsim_episodes {
     double  *res_final_rpos; /* [k][2] or NULL: robot position after the terminal step (parity evidence) */
 } crowdsim_episodes;
 
-/* Scenario generation request for crowdsim_reset. */
+/*
+ * Auto-reset with prefetched scenes (optional, pass NULL to crowdsim_step to disable).
+ * Every env slot owns a "next scene" buffer. crowdsim_prefetch_scenes (any stream, may overlap with steps) fills
+ * slots whose n_state is EMPTY and marks them READY; crowdsim_step, when an env's episode terminates, installs the
+ * READY scene into the live state in the same launch (fresh episode, global_time 0, velocities 0, accumulators
+ * cleared, ep_case = n_case) and marks the slot EMPTY again. If the scene is not ready yet the env is parked
+ * (active = 0, want = 1) and installed by a later step; EXHAUSTED slots (case queue empty) just go inactive.
+ * Single-writer protocol: only the generator moves EMPTY -> READY/EXHAUSTED, only the step kernel moves READY -> EMPTY.
+ * Requires crowdsim_state.active != NULL.
+ */
+#define CROWDSIM_SLOT_EMPTY     0
+#define CROWDSIM_SLOT_READY     1
+#define CROWDSIM_SLOT_EXHAUSTED 2
+typedef struct crowdsim_autoreset {
+    double *n_h_pos;     /* [B][N][2] next scene: human start positions */
+    double *n_h_goal;    /* [B][N][2] human goals */
+    double *n_h_attr;    /* [B][N][2] human radius, v_pref */
+    int32_t *n_case;     /* [B] case index of the prefetched scene (-1 = untracked) */
+    uint8_t *n_state;    /* [B] CROWDSIM_SLOT_* */
+    uint8_t *want;       /* [B] 1 = env finished and is waiting for a scene */
+    double circle_radius;  /* robot start/goal (0, -R) -> (0, R), crowd_sim.py:274 */
+    double robot_radius, robot_v_pref;
+} crowdsim_autoreset;
+
+/* Scenario generation request for crowdsim_reset / crowdsim_prefetch_scenes. */
 typedef struct crowdsim_reset_args {
     const uint8_t *mask;     /* [B] or NULL: reset only envs with mask[e] != 0 (NULL = all) */
     uint32_t *seed;          /* [B] MT19937 seed per env (crowd_sim.py:272-276: offset[phase] + case); after a masked env
@@ -143,6 +169,12 @@ typedef struct crowdsim_reset_args {
     double discomfort_dist;  /* 0.2 (min initial separation, crowd_sim.py:168) */
     int32_t randomize_attributes; /* env.config [env] randomize_attributes (agent.py:39-45) */
     uint32_t *mt_scratch;    /* [624][B] uint32 device scratch for the MT19937 states (caller-owned) */
+    /* Optional case work-queue (Explorer.run_k_episodes over k cases with fewer slots): when case_counter != NULL the
+     * seed of a generated scene is seed_base + c with c = atomicAdd(case_counter, 1); c >= case_total => no scene
+     * (prefetch marks the slot EXHAUSTED). `seed`/`seed_stride` are ignored then. */
+    int32_t *case_counter;
+    int32_t case_total;
+    uint32_t seed_base;
 } crowdsim_reset_args;
 
 /* Library / device probing (host only, no kernel launch). */
@@ -156,9 +188,9 @@ void crowdsim_debug_force_generic(int on);
 /* Tuning hook: envs packed per warp by the small-crowd step kernel (0 = built-in heuristic). */
 void crowdsim_debug_force_epw(int epw);
 
-/* One lockstep env-step for B envs. `ep` may be NULL. */
+/* One lockstep env-step for B envs. `ep` and `ar` may be NULL. */
 int crowdsim_step(const crowdsim_params *prm, int B, int N, crowdsim_state *st, crowdsim_step_io *io,
-                  crowdsim_episodes *ep, void *stream);
+                  crowdsim_episodes *ep, const crowdsim_autoreset *ar, void *stream);
 
 /* Robot ORCA action from the current state, no mutation: action_out[B][2]. */
 int crowdsim_orca_act(const crowdsim_params *prm, int B, int N, const crowdsim_state *st, double *action_out,
@@ -168,6 +200,9 @@ int crowdsim_orca_act(const crowdsim_params *prm, int B, int N, const crowdsim_s
  * when `ep` is given, clears the slot accumulators. Sets active[e] = 1 if `st->active` is present. */
 int crowdsim_reset(const crowdsim_reset_args *args, int B, int N, crowdsim_state *st, crowdsim_episodes *ep,
                    void *stream);
+
+/* Fill the EMPTY next-scene slots of `ar` (generator side of the auto-reset protocol above). `args->mask` is ignored. */
+int crowdsim_prefetch_scenes(const crowdsim_reset_args *args, int B, int N, const crowdsim_autoreset *ar, void *stream);
 
 /*
  * Rotated joint state of the CURRENT state for value-net policies: out[B][N][13] float32

@@ -85,18 +85,28 @@ void oracle_mt19937_doubles(uint32_t seed, int n, double *out)
 }
 
 /* ---------------- reset: crowd_sim.py:251-312, generators :155-207, agent.py:39-45 ---------------- */
-static void reset_one(const crowdsim_reset_args *a, int e, int N, crowdsim_state *st)
+/* seed of the next scene of slot e: per-slot seed (+ stride) or the shared case queue (0 = queue empty) */
+static int next_seed(const crowdsim_reset_args *a, int e, uint32_t *seed, int *case_id)
 {
-    mt_state rng; mt_seed(&rng, a->seed[e]);
+    if (a->case_counter) {
+        int c;
+        #pragma omp atomic capture
+        c = (*a->case_counter)++;
+        if (c >= a->case_total) return 0;
+        *seed = a->seed_base + (uint32_t)c; *case_id = c;
+        return 1;
+    }
+    *seed = a->seed[e];
     if (a->seed_stride) a->seed[e] += a->seed_stride;
-    double *hp = st->h_pos + (size_t)e * N * 2, *hv = st->h_vel + (size_t)e * N * 2;
-    double *hg = st->h_goal + (size_t)e * N * 2, *ha = st->h_attr + (size_t)e * N * 2;
-    /* crowd_sim.py:274 robot.set(0, -R, 0, R, 0, 0, pi/2) */
+    *case_id = -1;
+    return 1;
+}
+
+/* N humans by rejection sampling into hp/hg/ha ([N][2] each); crowd_sim.py:155-207, agent.py:39-45 */
+static void generate_scene(mt_state *rngp, const crowdsim_reset_args *a, int N, double *hp, double *hg, double *ha)
+{
+    mt_state rng = *rngp;
     const double rpx = 0.0, rpy = -a->circle_radius, rgx = 0.0, rgy = a->circle_radius;
-    st->r_pos[2 * e] = rpx; st->r_pos[2 * e + 1] = rpy; st->r_goal[2 * e] = rgx; st->r_goal[2 * e + 1] = rgy;
-    st->r_vel[2 * e] = 0.0; st->r_vel[2 * e + 1] = 0.0;
-    st->r_attr[2 * e] = a->robot_radius; st->r_attr[2 * e + 1] = a->robot_v_pref;
-    st->r_theta[e] = PI_D / 2; st->g_time[e] = 0.0;
     for (int i = 0; i < N; ++i) {
         double radius = a->human_radius, v_pref = a->human_v_pref;
         if (a->randomize_attributes) {            /* agent.py:44-45: v_pref first, then radius */
@@ -148,21 +158,65 @@ static void reset_one(const crowdsim_reset_args *a, int e, int N, crowdsim_state
             }
         }
         hp[2 * i] = px; hp[2 * i + 1] = py; hg[2 * i] = gx; hg[2 * i + 1] = gy;
-        hv[2 * i] = 0.0; hv[2 * i + 1] = 0.0; ha[2 * i] = radius; ha[2 * i + 1] = v_pref;
+        ha[2 * i] = radius; ha[2 * i + 1] = v_pref;
     }
-    if (st->active) st->active[e] = 1;
+    *rngp = rng;
 }
 
 int oracle_crowdsim_reset(const crowdsim_reset_args *args, int B, int N, crowdsim_state *st, crowdsim_episodes *ep)
 {
-    if (!args || !st || !args->seed || B < 0 || N < 0) return CROWDSIM_EINVAL;
+    if (!args || !st || (!args->seed && !args->case_counter) || B < 0 || N < 0) return CROWDSIM_EINVAL;
     #pragma omp parallel for schedule(static)
     for (int e = 0; e < B; ++e) {
         if (args->mask && !args->mask[e]) continue;
-        reset_one(args, e, N, st);
-        if (ep) { ep->ep_steps[e] = 0; ep->ep_return[e] = 0.0; ep->ep_too_close[e] = 0; ep->ep_min_dist_sum[e] = 0.0; }
+        uint32_t seed; int case_id;
+        if (!next_seed(args, e, &seed, &case_id)) { if (st->active) st->active[e] = 0; if (ep) ep->ep_case[e] = -1; continue; }
+        mt_state rng; mt_seed(&rng, seed);
+        /* crowd_sim.py:274 robot.set(0, -R, 0, R, 0, 0, pi/2) */
+        st->r_pos[2 * e] = 0.0; st->r_pos[2 * e + 1] = -args->circle_radius; st->r_goal[2 * e] = 0.0; st->r_goal[2 * e + 1] = args->circle_radius;
+        st->r_vel[2 * e] = 0.0; st->r_vel[2 * e + 1] = 0.0;
+        st->r_attr[2 * e] = args->robot_radius; st->r_attr[2 * e + 1] = args->robot_v_pref;
+        st->r_theta[e] = PI_D / 2; st->g_time[e] = 0.0;
+        generate_scene(&rng, args, N, st->h_pos + (size_t)e * N * 2, st->h_goal + (size_t)e * N * 2, st->h_attr + (size_t)e * N * 2);
+        for (int i = 0; i < 2 * N; ++i) st->h_vel[(size_t)e * N * 2 + i] = 0.0;
+        if (st->active) st->active[e] = 1;
+        if (ep) { ep->ep_steps[e] = 0; ep->ep_return[e] = 0.0; ep->ep_too_close[e] = 0; ep->ep_min_dist_sum[e] = 0.0;
+                  if (args->case_counter) ep->ep_case[e] = case_id; }
     }
     return 0;
+}
+
+/* generator side of the auto-reset protocol (include/crowdsim_b200.h) */
+int oracle_crowdsim_prefetch_scenes(const crowdsim_reset_args *args, int B, int N, const crowdsim_autoreset *ar)
+{
+    if (!args || !ar || (!args->seed && !args->case_counter)) return CROWDSIM_EINVAL;
+    #pragma omp parallel for schedule(static)
+    for (int e = 0; e < B; ++e) {
+        if (ar->n_state[e] != CROWDSIM_SLOT_EMPTY) continue;
+        uint32_t seed; int case_id;
+        if (!next_seed(args, e, &seed, &case_id)) { ar->n_state[e] = CROWDSIM_SLOT_EXHAUSTED; continue; }
+        mt_state rng; mt_seed(&rng, seed);
+        generate_scene(&rng, args, N, ar->n_h_pos + (size_t)e * N * 2, ar->n_h_goal + (size_t)e * N * 2, ar->n_h_attr + (size_t)e * N * 2);
+        ar->n_case[e] = case_id;
+        ar->n_state[e] = CROWDSIM_SLOT_READY;
+    }
+    return 0;
+}
+
+/* consumer side: install the READY scene of slot e into the live state, or park the env */
+static void autoreset_env(const crowdsim_autoreset *ar, int e, int N, crowdsim_state *st, crowdsim_episodes *ep)
+{
+    const uint8_t s = ar->n_state[e];
+    if (s != CROWDSIM_SLOT_READY) { st->active[e] = 0; ar->want[e] = (s == CROWDSIM_SLOT_EXHAUSTED) ? 0 : 1; return; }
+    const size_t o = (size_t)e * N * 2;
+    for (int i = 0; i < 2 * N; ++i) { st->h_pos[o + i] = ar->n_h_pos[o + i]; st->h_vel[o + i] = 0.0; st->h_goal[o + i] = ar->n_h_goal[o + i]; st->h_attr[o + i] = ar->n_h_attr[o + i]; }
+    st->r_pos[2 * e] = 0.0; st->r_pos[2 * e + 1] = -ar->circle_radius; st->r_goal[2 * e] = 0.0; st->r_goal[2 * e + 1] = ar->circle_radius;
+    st->r_vel[2 * e] = 0.0; st->r_vel[2 * e + 1] = 0.0; st->r_attr[2 * e] = ar->robot_radius; st->r_attr[2 * e + 1] = ar->robot_v_pref;
+    if (st->r_theta) st->r_theta[e] = PI_D / 2;
+    st->g_time[e] = 0.0;
+    if (ep) { ep->ep_steps[e] = 0; ep->ep_return[e] = 0.0; ep->ep_too_close[e] = 0; ep->ep_min_dist_sum[e] = 0.0; ep->ep_case[e] = ar->n_case[e]; }
+    st->active[e] = 1; ar->want[e] = 0;
+    ar->n_state[e] = CROWDSIM_SLOT_EMPTY;
 }
 
 /* ---------------- ORCA.predict: crowd_sim/envs/policy/orca.py:82-132 ---------------- */
@@ -216,7 +270,7 @@ void oracle_clear_stats(void) { memset(g_stats, 0, sizeof(g_stats)); }
 
 /* ---------------- step: crowd_sim/envs/crowd_sim.py:317-420 (update=True) + explorer.py:41-72 ---------------- */
 static void step_one(const crowdsim_params *p, int e, int N, crowdsim_state *st, crowdsim_step_io *io,
-                     crowdsim_episodes *ep, orc_stats *stats)
+                     crowdsim_episodes *ep, const crowdsim_autoreset *ar, orc_stats *stats)
 {
     double *hp = st->h_pos + (size_t)e * N * 2, *hv = st->h_vel + (size_t)e * N * 2;
     const double *hg = st->h_goal + (size_t)e * N * 2, *ha = st->h_attr + (size_t)e * N * 2;
@@ -285,22 +339,24 @@ static void step_one(const crowdsim_params *p, int e, int N, crowdsim_state *st,
                 ep->res_min_dist_sum[c] = ep->ep_min_dist_sum[e];
                 if (ep->res_final_rpos) { ep->res_final_rpos[2 * c] = rp[0]; ep->res_final_rpos[2 * c + 1] = rp[1]; }
             }
-            if (st->active) st->active[e] = 0;
+            if (st->active && !ar) st->active[e] = 0;
         }
     }
+    if (ar && done) autoreset_env(ar, e, N, st, ep);
 }
 
 int oracle_crowdsim_step(const crowdsim_params *prm, int B, int N, crowdsim_state *st, crowdsim_step_io *io,
-                         crowdsim_episodes *ep)
+                         crowdsim_episodes *ep, const crowdsim_autoreset *ar)
 {
     if (!prm || !st || !io || B < 0 || N < 0) return CROWDSIM_EINVAL;
+    if (ar && !st->active) return CROWDSIM_EINVAL;
     if (N > CROWDSIM_MAX_HUMANS || prm->max_neighbors > CROWDSIM_MAX_NEIGHBORS) return CROWDSIM_EUNSUPPORTED;
     long s0 = 0, s1 = 0, s2 = 0, s3 = 0;
     #pragma omp parallel for schedule(static) reduction(+:s0,s1,s2,s3)
     for (int e = 0; e < B; ++e) {
-        if (st->active && !st->active[e]) continue;
+        if (st->active && !st->active[e]) { if (ar && ar->want[e]) autoreset_env(ar, e, N, st, ep); continue; }
         orc_stats stats = {0, 0, 0, 0};
-        step_one(prm, e, N, st, io, ep, &stats);
+        step_one(prm, e, N, st, io, ep, ar, &stats);
         s0 += stats.solves; s1 += stats.lines; s2 += stats.lp1_calls; s3 += stats.lp3_calls;
     }
     g_stats[0] += s0; g_stats[1] += s1; g_stats[2] += s2; g_stats[3] += s3;

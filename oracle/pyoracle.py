@@ -115,24 +115,56 @@ class HostEpisodes(object):
                              _ptr(self.res_too_close), _ptr(self.res_min_dist_sum), _ptr(self.res_final_rpos))
 
 
+class HostAutoReset(object):
+    """crowdsim_autoreset on host arrays (next-scene slot per env)."""
+
+    def __init__(self, B, N, circle_radius=4.0, robot_radius=0.3, robot_v_pref=1.0):
+        self.n_h_pos = np.zeros((B, N, 2)); self.n_h_goal = np.zeros((B, N, 2)); self.n_h_attr = np.zeros((B, N, 2))
+        self.n_case = np.full(B, -1, dtype=np.int32)
+        self.n_state = np.zeros(B, dtype=np.uint8); self.want = np.zeros(B, dtype=np.uint8)
+        self.circle_radius, self.robot_radius, self.robot_v_pref = circle_radius, robot_radius, robot_v_pref
+
+    def struct(self):
+        return _abi.AutoReset(_ptr(self.n_h_pos), _ptr(self.n_h_goal), _ptr(self.n_h_attr), _ptr(self.n_case),
+                              _ptr(self.n_state), _ptr(self.want), self.circle_radius, self.robot_radius, self.robot_v_pref)
+
+
+def _reset_args(seeds, rule, mask, circle_radius, square_width, human_radius, human_v_pref, robot_radius, robot_v_pref,
+                discomfort_dist, randomize_attributes, seed_stride, case_counter, case_total, seed_base):
+    return _abi.ResetArgs(_ptr(mask), _ptr(seeds), int(seed_stride), _abi.RULES[rule], circle_radius, square_width,
+                          human_radius, human_v_pref, robot_radius, robot_v_pref, discomfort_dist,
+                          int(randomize_attributes), None, _ptr(case_counter), int(case_total), int(seed_base))
+
+
+def prefetch(ar, B, N, seeds=None, rule='circle_crossing', circle_radius=4.0, square_width=10.0, human_radius=0.3,
+             human_v_pref=1.0, robot_radius=0.3, robot_v_pref=1.0, discomfort_dist=0.2, randomize_attributes=False,
+             seed_stride=0, case_counter=None, case_total=0, seed_base=0):
+    a = _reset_args(seeds, rule, None, circle_radius, square_width, human_radius, human_v_pref, robot_radius,
+                    robot_v_pref, discomfort_dist, randomize_attributes, seed_stride, case_counter, case_total, seed_base)
+    s = ar.struct()
+    rc = lib().oracle_crowdsim_prefetch_scenes(C.byref(a), B, N, C.byref(s))
+    assert rc == 0, rc
+
+
 def reset(st, seeds, rule='circle_crossing', mask=None, ep=None, circle_radius=4.0, square_width=10.0,
           human_radius=0.3, human_v_pref=1.0, robot_radius=0.3, robot_v_pref=1.0, discomfort_dist=0.2,
-          randomize_attributes=False, seed_stride=0):
+          randomize_attributes=False, seed_stride=0, case_counter=None, case_total=0, seed_base=0):
     """seeds: uint32 array; with seed_stride != 0 it must be a writable contiguous uint32 array (advanced in place)."""
-    if not (isinstance(seeds, np.ndarray) and seeds.dtype == np.uint32 and seeds.flags['C_CONTIGUOUS']):
+    if seeds is not None and not (isinstance(seeds, np.ndarray) and seeds.dtype == np.uint32 and seeds.flags['C_CONTIGUOUS']):
         seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
     mask = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
-    a = _abi.ResetArgs(_ptr(mask), _ptr(seeds), int(seed_stride), _abi.RULES[rule], circle_radius, square_width, human_radius,
-                       human_v_pref, robot_radius, robot_v_pref, discomfort_dist, int(randomize_attributes), None)
+    a = _reset_args(seeds, rule, mask, circle_radius, square_width, human_radius, human_v_pref, robot_radius,
+                    robot_v_pref, discomfort_dist, randomize_attributes, seed_stride, case_counter, case_total, seed_base)
     s = st.struct(); e = ep.struct() if ep is not None else None
     rc = lib().oracle_crowdsim_reset(C.byref(a), st.B, st.N, C.byref(s), C.byref(e) if e is not None else None)
     assert rc == 0, rc
 
 
-def step(prm, st, io, ep=None):
+def step(prm, st, io, ep=None, ar=None):
     s, i = st.struct(), io.struct(); e = ep.struct() if ep is not None else None
+    a = ar.struct() if ar is not None else None
     rc = lib().oracle_crowdsim_step(C.byref(prm), st.B, st.N, C.byref(s), C.byref(i),
-                                    C.byref(e) if e is not None else None)
+                                    C.byref(e) if e is not None else None, C.byref(a) if a is not None else None)
     assert rc == 0, rc
 
 

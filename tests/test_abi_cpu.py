@@ -35,7 +35,8 @@ def test_exports_every_declared_symbol(lib):
 def test_struct_layout_matches_header(tmp_path):
     from crowdnav_b200 import _abi
     pairs = [('crowdsim_params', _abi.Params), ('crowdsim_state', _abi.State), ('crowdsim_step_io', _abi.StepIO),
-             ('crowdsim_episodes', _abi.Episodes), ('crowdsim_reset_args', _abi.ResetArgs)]
+             ('crowdsim_episodes', _abi.Episodes), ('crowdsim_reset_args', _abi.ResetArgs),
+             ('crowdsim_autoreset', _abi.AutoReset)]
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "%s"' % HEADER, 'int main(void){']
     for cname, ct in pairs:
         lines.append('printf("%s %%zu", sizeof(%s));' % (cname, cname))
@@ -60,13 +61,14 @@ def test_argument_validation_without_gpu(lib):
     from crowdnav_b200 import _abi
     prm = _abi.Params(0.25, 25.0, 1.0, -0.25, 0.2, 0.5, 10.0, 5.0, 10, 0.0, 0.0, 0, _abi.ROBOT_ORCA)
     st, io = _abi.State(), _abi.StepIO()
-    assert lib.crowdsim_step(None, 1, 5, C.byref(st), C.byref(io), None, None) == -1
-    assert lib.crowdsim_step(C.byref(prm), 1, 5, C.byref(st), C.byref(io), None, None) == -1        # NULL arrays
-    assert lib.crowdsim_step(C.byref(prm), 1, _abi.MAX_HUMANS + 1, C.byref(st), C.byref(io), None, None) == -2
+    assert lib.crowdsim_step(None, 1, 5, C.byref(st), C.byref(io), None, None, None) == -1
+    assert lib.crowdsim_step(C.byref(prm), 1, 5, C.byref(st), C.byref(io), None, None, None) == -1        # NULL arrays
+    assert lib.crowdsim_step(C.byref(prm), 1, _abi.MAX_HUMANS + 1, C.byref(st), C.byref(io), None, None, None) == -2
     prm.max_neighbors = _abi.MAX_NEIGHBORS + 1
-    assert lib.crowdsim_step(C.byref(prm), 1, 5, C.byref(st), C.byref(io), None, None) == -2
+    assert lib.crowdsim_step(C.byref(prm), 1, 5, C.byref(st), C.byref(io), None, None, None) == -2
     prm.max_neighbors = 10
     assert lib.crowdsim_reset(None, 1, 5, C.byref(st), None, None) == -1
+    assert lib.crowdsim_prefetch_scenes(None, 1, 5, None, None) == -1
     assert lib.crowdsim_pack_joint(1, 5, C.byref(st), 0, None, None) == -1
     assert lib.crowdsim_lookahead_pack(C.byref(prm), 1, 5, C.byref(st), None, 81, 0, None, None, None) == -1
     assert lib.crowdsim_orca_act(C.byref(prm), 1, 5, C.byref(st), None, None) == -1

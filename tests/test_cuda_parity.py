@@ -287,3 +287,71 @@ def test_large_batch_linearity(cuda_env, oracle):
         for f in ('h_pos', 'h_vel', 'r_pos', 'g_time'):
             assert torch.equal(getattr(env.state, f), getattr(s2.state, f)[idx]), (B, f)
         assert torch.equal(env.info, s2.info[idx]) and torch.equal(env.reward, s2.reward[idx])
+
+
+def test_autoreset_install_bit_exact(cuda_env, oracle):
+    """Consumer side of the auto-reset protocol: with identical prefetched scenes (generated by the oracle, copied into
+    the device slots after every step) GPU and oracle stay bit-identical through hundreds of episode boundaries,
+    including parked envs (slot not ready) and queue exhaustion."""
+    for N, generic in [(5, 0), (5, 1), (12, 0)]:
+        from crowdnav_b200 import _abi
+        _abi.load().crowdsim_debug_force_generic(generic)
+        B, k = 96, 700
+        prm = oracle.default_params()
+        host = oracle.HostState(B, N); io = oracle.HostStepIO(B); hep = oracle.HostEpisodes(B, k); har = oracle.HostAutoReset(B, N)
+        counter = np.zeros(1, dtype=np.int32)
+        q = dict(case_counter=counter, case_total=k, seed_base=2000)
+        oracle.reset(host, None, ep=hep, **q)
+        env = cuda_env(B, N)
+        ep = env.track_episodes(k)
+        env.enable_autoreset()
+        env.state.load_host(host)
+        ep.ep_case.copy_(torch.from_numpy(hep.ep_case))
+        it = 0
+        while (host.active.any() or har.want.any()) and it < 3000:
+            if it % 3 == 0:                                  # prefetch only every third step: some envs find an EMPTY slot and park
+                oracle.prefetch(har, B, N, **q)
+            env.autoreset.load_host(har)
+            env.step()
+            oracle.step(prm, host, io, hep, har)
+            torch.cuda.synchronize()
+            d = env.autoreset.to_host()
+            assert np.array_equal(d['n_state'], har.n_state) and np.array_equal(d['want'], har.want), it
+            assert np.array_equal(env.state.active.cpu().numpy(), host.active), it
+            if it % 25 == 0:
+                _assert_state_equal(env, host, what='autoreset N=%d it=%d' % (N, it))
+            it += 1
+        assert int(counter[0]) >= k
+        _assert_state_equal(env, host, what='autoreset final')
+        for f in ('res_info', 'res_steps', 'res_time', 'res_return', 'res_too_close', 'res_min_dist_sum', 'res_final_rpos'):
+            assert np.array_equal(getattr(ep, f).cpu().numpy(), getattr(hep, f)), f
+
+
+@pytest.mark.parametrize('slots', [64, 500])
+def test_autoreset_device_prefetch_reproduces_suite(cuda_env, slots):
+    """Full device pipeline: scenes prefetched ON DEVICE from the shared case queue (side stream), installed by the step
+    kernel. 500 test cases through `slots` slots: terminal class and step count exact, final position within 1e-5."""
+    N = 5
+    cases = load_golden('suite_circle5_invisible')['cases']
+    k = len(cases)
+    env = cuda_env(slots, N)
+    ep = env.track_episodes(k)
+    env.set_case_queue(0, k, 'test')
+    env.enable_autoreset('circle_crossing')
+    env.reset_seeds(rule='circle_crossing', use_queue=True)
+    side = torch.cuda.Stream()
+    for it in range(4000):
+        if it % 2 == 0:
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                env.prefetch()                                # overlaps with the following steps
+        env.step()
+        if it % 64 == 63 and int(env.state.active.sum()) == 0 and int(env.autoreset.want.sum()) == 0:
+            break
+    torch.cuda.synchronize()
+    assert int(env.state.active.sum()) == 0
+    info = ep.res_info.cpu().numpy(); steps = ep.res_steps.cpu().numpy(); frp = ep.res_final_rpos.cpu().numpy()
+    assert [int(x) for x in info] == [c['info'] for c in cases]
+    assert [int(x) for x in steps] == [c['steps'] for c in cases]
+    fr = np.array([scene_arrays(c['final'])[0][:2] for c in cases])
+    assert np.abs(frp - fr).max() < 1e-5

@@ -180,3 +180,30 @@ def test_oracle_workload_statistics(oracle):
     assert solves == 6 * 15190
     assert abs(lines / solves - 4.17) < 0.01
     assert abs(lp3 / solves - 0.0458) < 0.001
+
+
+@pytest.mark.parametrize('slots', [7, 64, 500])
+def test_autoreset_case_queue_reproduces_suite(oracle, slots):
+    """Auto-reset protocol + shared case queue (include/crowdsim_b200.h): 500 test cases streamed through `slots` env
+    slots (prefetch -> install on termination) give, per case, exactly the reference's episode."""
+    N = 5
+    cases = load_golden('suite_circle5_invisible')['cases']
+    k = len(cases)
+    prm = oracle.default_params()
+    st = oracle.HostState(slots, N); io = oracle.HostStepIO(slots); ep = oracle.HostEpisodes(slots, k)
+    ar = oracle.HostAutoReset(slots, N)
+    counter = np.zeros(1, dtype=np.int32)
+    q = dict(case_counter=counter, case_total=k, seed_base=1000)
+    oracle.reset(st, None, ep=ep, **q)                       # first `slots` cases straight into the live state
+    oracle.prefetch(ar, slots, N, **q)
+    for it in range(100000):
+        if not st.active.any() and not ar.want.any():
+            break
+        oracle.step(prm, st, io, ep, ar)
+        oracle.prefetch(ar, slots, N, **q)
+    assert int(counter[0]) >= k and not st.active.any()
+    for i, c in enumerate(cases):
+        assert ep.res_info[i] == c['info'] and ep.res_steps[i] == c['steps'], c['case']
+        assert ep.res_return[i] == float(c['return'])
+        r, _ = scene_arrays(c['final'])
+        assert (ep.res_final_rpos[i] == r[:2]).all()
