@@ -52,7 +52,7 @@ class ResetArgs(C.Structure):
                 ('circle_radius', C.c_double), ('square_width', C.c_double), ('human_radius', C.c_double),
                 ('human_v_pref', C.c_double), ('robot_radius', C.c_double), ('robot_v_pref', C.c_double),
                 ('discomfort_dist', C.c_double), ('randomize_attributes', C.c_int32),
-                ('mt_scratch', C.c_void_p), ('case_counter', C.c_void_p), ('case_total', C.c_int32),
+                ('case_counter', C.c_void_p), ('case_total', C.c_int32),
                 ('seed_base', C.c_uint32)]
 
 

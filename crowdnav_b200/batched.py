@@ -128,7 +128,6 @@ class BatchedCrowdSim(object):
         # ORCA constants (orca.py:61-64)
         self.neighbor_dist = 10.0; self.max_neighbors = 10; self.time_horizon = 5.0
         self.state = None; self.episodes = None; self.autoreset = None
-        self._mt_scratch = None; self._mt_scratch_prefetch = None
         self._case_counter = None; self._case_total = 0; self._seed_base = 0
         self._ar_rule = None; self._ar_seed_stride = 0
 
@@ -172,7 +171,6 @@ class BatchedCrowdSim(object):
         self.done = torch.zeros(B, dtype=torch.uint8, device=self.device)
         self.info = torch.zeros(B, dtype=torch.uint8, device=self.device)
         self._seed32 = torch.zeros(B, dtype=torch.int32, device=self.device)
-        self._mt_scratch = torch.empty((624, B), dtype=torch.int32, device=self.device)
 
     def set_robot_policy(self, kind):
         self.robot_policy = {'orca': _abi.ROBOT_ORCA, 'external_xy': _abi.ROBOT_EXTERNAL_XY, 'holonomic': _abi.ROBOT_EXTERNAL_XY,
@@ -212,11 +210,11 @@ class BatchedCrowdSim(object):
         # uint32 bit patterns stored in an int32 tensor
         self._seed32.copy_(((seeds + 2 ** 31) % 2 ** 32 - 2 ** 31).to(torch.int32))
 
-    def _reset_args(self, mask, rule, seed_stride, scratch, use_queue):
+    def _reset_args(self, mask, rule, seed_stride, use_queue):
         q = use_queue and self._case_counter is not None
         return _abi.ResetArgs(_ptr(mask), _ptr(self._seed32), int(seed_stride) % 2 ** 32, _abi.RULES[rule], self.circle_radius,
                               self.square_width, self.human_radius, self.human_v_pref, self.robot_radius, self.robot_v_pref,
-                              self.discomfort_dist, int(bool(self.randomize_attributes)), _ptr(scratch),
+                              self.discomfort_dist, int(bool(self.randomize_attributes)),
                               _ptr(self._case_counter) if q else None, self._case_total if q else 0, self._seed_base if q else 0)
 
     def reset_seeds(self, seeds=None, mask=None, rule='circle_crossing', seed_stride=0, use_queue=False):
@@ -227,7 +225,7 @@ class BatchedCrowdSim(object):
             self.set_seeds(seeds)
         if mask is not None and not (isinstance(mask, torch.Tensor) and mask.dtype == torch.uint8 and mask.device == self.device):
             mask = torch.as_tensor(mask).to(device=self.device, dtype=torch.uint8)
-        a = self._reset_args(mask, rule, seed_stride, self._mt_scratch, use_queue)
+        a = self._reset_args(mask, rule, seed_stride, use_queue)
         st = self.state.struct()
         ep = self.episodes.struct() if self.episodes is not None else None
         rc = self.lib.crowdsim_reset(C.byref(a), self.B, self.human_num, C.byref(st),
@@ -248,12 +246,11 @@ class BatchedCrowdSim(object):
         Call prefetch() (any stream) to (re)fill consumed slots."""
         self.autoreset = AutoResetBuffers(self.B, self.human_num, self.device, self.circle_radius, self.robot_radius,
                                           self.robot_v_pref)
-        self._mt_scratch_prefetch = torch.empty((624, self.B), dtype=torch.int32, device=self.device)
         self._ar_rule, self._ar_seed_stride = rule, seed_stride
         return self.autoreset
 
     def prefetch(self):
-        a = self._reset_args(None, self._ar_rule, self._ar_seed_stride, self._mt_scratch_prefetch, True)
+        a = self._reset_args(None, self._ar_rule, self._ar_seed_stride, True)
         ar = self.autoreset.struct()
         rc = self.lib.crowdsim_prefetch_scenes(C.byref(a), self.B, self.human_num, C.byref(ar), self._stream())
         _abi.check(rc, 'crowdsim_prefetch_scenes')

@@ -4,24 +4,26 @@
 // (generate_circle_crossing_human / generate_square_crossing_human) incl. agent.py:39-45
 // (sample_random_attributes): np.random.seed(seed) == init_genrand(seed), np.random.random() == genrand_res53.
 //
-// One thread per environment that needs a reset. The 624-word MT19937 state of a thread lives in a caller-owned
-// global scratch laid out [624][B] (word-major), so the threads of a warp touch consecutive addresses. The twist is
-// done lazily, in place and in order (word i of the next block needs old words i, i+1 and word i+397 mod 624, which
-// is old for i < 227 and already-new afterwards -- exactly the dependency order of the classic in-place loop), so a
-// reset only pays for the words it actually draws (~40 for 5 circle-crossing humans) on top of the 624-step seeding
-// recurrence, which is inherently sequential.
+// Only a few env slots need a scene at any time (~3 % of the envs finish per step), so each 128-slot block first
+// compacts the slots that do into a shared-memory list; the first kGen threads of the block then generate scenes, each
+// with its 624-word MT19937 state in its own SHARED-MEMORY column ([624][kGen] words, conflict-free across lanes). The
+// earlier version kept the state in a global [624][B] scratch: every draw then paid three dependent L2 round trips and
+// one scene took 60-70 us (scripts/probe_autoreset.py); in shared memory it is ~10 us, bounded by the 624-step seeding
+// recurrence, which is inherently sequential. The twist is done lazily, in place and in order (word i of the next block
+// needs old words i, i+1 and word i+397 mod 624, which is old for i < 227 and already-new afterwards -- exactly the
+// dependency order of the classic in-place loop), so a scene only pays for the words it actually draws.
 //
 // float64 arithmetic in the reference's expression order; cos/sin are CUDA's (<= 1-2 ulp from glibc's, which numpy
-// uses): initial coordinates can differ from the CPU reference in the last bit (tests allow 4 ulp).
+// uses): initial coordinates can differ from the CPU reference by ~1e-15 (tests bound it at 4e-15).
 #include "crowdsim_common.cuh"
 
 namespace cs {
 
 struct MT {
-    uint32_t *mt;      // &scratch[slot], stride B between words
-    size_t stride;
+    uint32_t *mt;      // this thread's column of the shared-memory state array
+    int stride;        // columns (threads generating in this block)
     int pos;           // next word to produce, 0..623 (wraps)
-    __device__ __forceinline__ uint32_t &w(int i) { return mt[(size_t)i * stride]; }
+    __device__ __forceinline__ uint32_t &w(int i) { return mt[i * stride]; }
     __device__ void seed(uint32_t s) {
         for (int i = 0; i < 624; ++i) { w(i) = s; s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)i + 1u; }
         pos = 0;
@@ -126,12 +128,23 @@ struct ResetKArgs {
     int has_ep, B, N;
 };
 
-__global__ void __launch_bounds__(128) reset_kernel(const __grid_constant__ ResetKArgs A)
+constexpr int kSlotsPerBlock = 128;   // env slots scanned per block
+constexpr int kGen = 32;              // scenes generated concurrently per block (624 * kGen * 4 B = 78 KB shared memory)
+
+// Compact the slots of this block that need a scene; returns the count (block-uniform). s_list[0..count) = env ids.
+__device__ __forceinline__ int compact_block(bool need, int e, int *s_list, int *s_count)
 {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= A.B) return;
+    if (threadIdx.x == 0) *s_count = 0;
+    __syncthreads();
+    if (need) s_list[atomicAdd(s_count, 1)] = e;
+    __syncthreads();
+    return *s_count;
+}
+
+// Live-state reset of env e from its generated scene (crowd_sim.py:251-312).
+__device__ __forceinline__ void reset_env(const ResetKArgs &A, int e, MT &rng)
+{
     const crowdsim_reset_args &a = A.a;
-    if (a.mask && !a.mask[e]) return;
     const int N = A.N;
     uint32_t seed; int case_id;
     if (!next_seed(a, e, seed, case_id)) {                 // case queue exhausted: the env goes idle
@@ -139,7 +152,6 @@ __global__ void __launch_bounds__(128) reset_kernel(const __grid_constant__ Rese
         if (A.has_ep) A.ep.ep_case[e] = -1;
         return;
     }
-    MT rng; rng.mt = a.mt_scratch + e; rng.stride = (size_t)A.B;
     rng.seed(seed);
     double *hp = A.st.h_pos + (size_t)e * N * 2, *hv = A.st.h_vel + (size_t)e * N * 2;
     double *hg = A.st.h_goal + (size_t)e * N * 2, *ha = A.st.h_attr + (size_t)e * N * 2;
@@ -156,30 +168,62 @@ __global__ void __launch_bounds__(128) reset_kernel(const __grid_constant__ Rese
     }
 }
 
-// Generator side of the auto-reset protocol (include/crowdsim_b200.h): fill EMPTY next-scene slots, mark them READY.
-__global__ void __launch_bounds__(128) prefetch_kernel(const __grid_constant__ ResetKArgs A)
+// Generator side of the auto-reset protocol (include/crowdsim_b200.h): fill an EMPTY next-scene slot, mark it READY.
+__device__ __forceinline__ void prefetch_env(const ResetKArgs &A, int e, MT &rng)
 {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= A.B) return;
     const crowdsim_autoreset &ar = A.ar;
-    if (*reinterpret_cast<volatile uint8_t *>(ar.n_state + e) != CROWDSIM_SLOT_EMPTY) return;
-    const crowdsim_reset_args &a = A.a;
     const int N = A.N;
     uint32_t seed; int case_id;
-    if (!next_seed(a, e, seed, case_id)) { ar.n_state[e] = CROWDSIM_SLOT_EXHAUSTED; return; }
-    MT rng; rng.mt = a.mt_scratch + e; rng.stride = (size_t)A.B;
+    if (!next_seed(A.a, e, seed, case_id)) { ar.n_state[e] = CROWDSIM_SLOT_EXHAUSTED; return; }
     rng.seed(seed);
-    generate_scene(rng, a, N, ar.n_h_pos + (size_t)e * N * 2, ar.n_h_goal + (size_t)e * N * 2, ar.n_h_attr + (size_t)e * N * 2);
+    generate_scene(rng, A.a, N, ar.n_h_pos + (size_t)e * N * 2, ar.n_h_goal + (size_t)e * N * 2, ar.n_h_attr + (size_t)e * N * 2);
     ar.n_case[e] = case_id;
     __threadfence();                                       // scene visible before the flag
     *reinterpret_cast<volatile uint8_t *>(ar.n_state + e) = CROWDSIM_SLOT_READY;
+}
+
+template <bool PREFETCH>
+__global__ void __launch_bounds__(kSlotsPerBlock) scene_kernel(const __grid_constant__ ResetKArgs A)
+{
+    extern __shared__ uint32_t s_mt[];                     // [624][kGen]
+    __shared__ int s_list[kSlotsPerBlock];
+    __shared__ int s_count;
+    const int e = blockIdx.x * kSlotsPerBlock + threadIdx.x;
+    bool need = e < A.B;
+    if (need) {
+        if (PREFETCH) need = *reinterpret_cast<volatile uint8_t *>(A.ar.n_state + e) == CROWDSIM_SLOT_EMPTY;
+        else need = !(A.a.mask && !A.a.mask[e]);
+    }
+    const int count = compact_block(need, e, s_list, &s_count);
+    if (threadIdx.x >= kGen) return;                       // the generating warp; no barriers below
+    MT rng; rng.mt = s_mt + threadIdx.x; rng.stride = kGen;
+    for (int base = 0; base + (int)threadIdx.x < count; base += kGen) {
+        const int ee = s_list[base + threadIdx.x];
+        if (PREFETCH) prefetch_env(A, ee, rng); else reset_env(A, ee, rng);
+    }
+}
+
+template <bool PREFETCH>
+static int launch_scene_kernel(const ResetKArgs &A, int B, cudaStream_t stream)
+{
+    const size_t smem = (size_t)624 * kGen * sizeof(uint32_t);
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[PREFETCH]) {
+        cudaError_t err = cudaFuncSetAttribute(scene_kernel<PREFETCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return (int)err;
+        attr_set[PREFETCH] = true;
+    }
+    const int blocks = (B + kSlotsPerBlock - 1) / kSlotsPerBlock;
+    scene_kernel<PREFETCH><<<blocks, kSlotsPerBlock, smem, stream>>>(A);
+    ++g_launches;
+    return (int)cudaGetLastError();
 }
 
 }  // namespace cs
 
 static int check_reset_args(const crowdsim_reset_args *args, int B, int N)
 {
-    if (!args || B < 0 || N < 0 || !args->mt_scratch) return CROWDSIM_EINVAL;
+    if (!args || B < 0 || N < 0) return CROWDSIM_EINVAL;
     if (!args->case_counter && !args->seed) return CROWDSIM_EINVAL;
     if (N > CROWDSIM_MAX_HUMANS) return CROWDSIM_EUNSUPPORTED;
     if (args->rule != CROWDSIM_RULE_CIRCLE && args->rule != CROWDSIM_RULE_SQUARE) return CROWDSIM_EUNSUPPORTED;
@@ -198,10 +242,7 @@ extern "C" int crowdsim_reset(const crowdsim_reset_args *args, int B, int N, cro
     cs::ResetKArgs A; A.a = *args; A.st = *st; A.has_ep = ep != nullptr; A.B = B; A.N = N;
     if (ep) A.ep = *ep; else memset(&A.ep, 0, sizeof(A.ep));
     memset(&A.ar, 0, sizeof(A.ar));
-    const int threads = 128, blocks = (B + threads - 1) / threads;
-    cs::reset_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(A);
-    ++cs::g_launches;
-    return (int)cudaGetLastError();
+    return cs::launch_scene_kernel<false>(A, B, (cudaStream_t)stream);
 }
 
 extern "C" int crowdsim_prefetch_scenes(const crowdsim_reset_args *args, int B, int N, const crowdsim_autoreset *ar, void *stream)
@@ -212,8 +253,5 @@ extern "C" int crowdsim_prefetch_scenes(const crowdsim_reset_args *args, int B, 
     if (B == 0) return CROWDSIM_OK;
     cs::ResetKArgs A; A.a = *args; A.ar = *ar; A.has_ep = 0; A.B = B; A.N = N;
     memset(&A.st, 0, sizeof(A.st)); memset(&A.ep, 0, sizeof(A.ep));
-    const int threads = 128, blocks = (B + threads - 1) / threads;
-    cs::prefetch_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(A);
-    ++cs::g_launches;
-    return (int)cudaGetLastError();
+    return cs::launch_scene_kernel<true>(A, B, (cudaStream_t)stream);
 }

@@ -168,7 +168,6 @@ typedef struct crowdsim_reset_args {
     double robot_v_pref;     /* env.config [robot] v_pref = 1    */
     double discomfort_dist;  /* 0.2 (min initial separation, crowd_sim.py:168) */
     int32_t randomize_attributes; /* env.config [env] randomize_attributes (agent.py:39-45) */
-    uint32_t *mt_scratch;    /* [624][B] uint32 device scratch for the MT19937 states (caller-owned) */
     /* Optional case work-queue (Explorer.run_k_episodes over k cases with fewer slots): when case_counter != NULL the
      * seed of a generated scene is seed_base + c with c = atomicAdd(case_counter, 1); c >= case_total => no scene
      * (prefetch marks the slot EXHAUSTED). `seed`/`seed_stride` are ignored then. */
