@@ -47,14 +47,17 @@ __global__ void __launch_bounds__(128) step_flat_kernel(const __grid_constant__ 
     const int ebase = le * L;                               // first lane of my env
     const int e = (blockIdx.x * WPB + wib) * EPW + le;
     const bool is_robot = (a == N);
-    bool live = (le < EPW) && (e < A.B);
-    if (live && A.st.active) live = (A.st.active[e] != 0);
+    const bool env_ok = (le < EPW) && (e < A.B);
     if (COMPACT && tid == 0) s_qcount = 0;
 
-    // ---- own agent: coalesced 16-byte loads ----
+    // ---- all global loads of the step are issued up front, unconditionally for valid envs, so that they overlap into ONE
+    // DRAM round trip (active flag -> state -> episode accumulators / slot state used to be dependent ones) ----
     double2 pos = make_double2(0, 0), vel = pos, goal = pos, attr = make_double2(0.3, 1.0);
     double theta = 0, gtime = 0; double2 ext = make_double2(0, 0);
-    if (live) {
+    uint8_t act_flag = 1, slot_state = 0, want_flag = 0;
+    int ep_t = 0, ep_tc = 0, ep_c = -1; double ep_ret = 0, ep_mds = 0;
+    if (env_ok) {
+        if (A.st.active) act_flag = A.st.active[e];
         if (!is_robot) {
             const size_t i = (size_t)e * N + a;
             pos = ld2(A.st.h_pos, i); vel = ld2(A.st.h_vel, i); goal = ld2(A.st.h_goal, i); attr = ld2(A.st.h_attr, i);
@@ -63,8 +66,11 @@ __global__ void __launch_bounds__(128) step_flat_kernel(const __grid_constant__ 
             gtime = A.st.g_time[e];
             if (k.robot_policy == CROWDSIM_ROBOT_EXTERNAL_ROT) theta = A.st.r_theta[e];
             if (k.robot_policy != CROWDSIM_ROBOT_ORCA) ext = ld2(A.io.action, e);
+            if (A.has_ep) { ep_t = A.ep.ep_steps[e]; ep_ret = A.ep.ep_return[e]; ep_tc = A.ep.ep_too_close[e]; ep_mds = A.ep.ep_min_dist_sum[e]; ep_c = A.ep.ep_case[e]; }
+            if (A.has_ar) { slot_state = *reinterpret_cast<volatile uint8_t *>(A.ar.n_state + e); want_flag = A.ar.want[e]; }
         }
     }
+    const bool live = env_ok && (act_flag != 0);
     if constexpr (STAGE == 1) {            // loads + stores only
         if (live && !is_robot) { const size_t i = (size_t)e * N + a; st2(A.st.h_pos, i, pos); st2(A.st.h_vel, i, make_double2(vel.x + goal.x * 0, vel.y + attr.x * 0)); }
         if (live && is_robot) { st2(A.st.r_pos, e, pos); A.st.g_time[e] = gtime + ext.x * 0 + theta * 0; }
@@ -196,7 +202,6 @@ __global__ void __launch_bounds__(128) step_flat_kernel(const __grid_constant__ 
 
     // ---- human lanes: swept-segment clearance (crowd_sim.py:333-345) + Euler step (agent.py:122-135) ----
     const double dt = k.time_step;
-    const bool env_ok = (le < EPW) && (e < A.B);
     double closest = 0.0;
     if (live && !is_robot) {
         const double px = pos.x - Rpx, py = pos.y - Rpy;
@@ -239,14 +244,14 @@ __global__ void __launch_bounds__(128) step_flat_kernel(const __grid_constant__ 
             A.io.reward[e] = reward; A.io.dmin[e] = dmin; A.io.done[e] = done ? 1 : 0; A.io.info[e] = (uint8_t)info;
             if (A.has_ep) {
                 const crowdsim_episodes &ep = A.ep;
-                const int t = ep.ep_steps[e];
+                const int t = ep_t;
                 const double disc = (t < ep.discount_len) ? ep.discount[t] : 0.0;
-                const double ret = ep.ep_return[e] + disc * reward;
-                int tc = ep.ep_too_close[e]; double mds = ep.ep_min_dist_sum[e];
+                const double ret = ep_ret + disc * reward;
+                int tc = ep_tc; double mds = ep_mds;
                 if (info == CROWDSIM_INFO_DANGER) { tc += 1; mds += dmin; ep.ep_too_close[e] = tc; ep.ep_min_dist_sum[e] = mds; }
                 ep.ep_return[e] = ret; ep.ep_steps[e] = t + 1;
                 if (done) {
-                    const int cs_ = ep.ep_case[e];
+                    const int cs_ = ep_c;
                     if (cs_ >= 0) {
                         ep.res_info[cs_] = (uint8_t)info; ep.res_steps[cs_] = t + 1;
                         ep.res_time[cs_] = (info == CROWDSIM_INFO_TIMEOUT) ? k.time_limit : ntime;
@@ -257,7 +262,7 @@ __global__ void __launch_bounds__(128) step_flat_kernel(const __grid_constant__ 
                 }
             }
         }
-        if (A.has_ar) install = ar_decide(A, e, live && done, !live && A.ar.want[e] != 0);
+        if (A.has_ar) install = ar_decide(A, e, slot_state, live && done, !live && want_flag != 0);
     }
     if (A.has_ar) {                                          // warp-uniform
         install = __shfl_sync(CS_FULL, install, rl) && env_ok;

@@ -33,10 +33,11 @@ struct StepArgs {
 
 // ---- auto-reset protocol, consumer side (include/crowdsim_b200.h: crowdsim_autoreset) ----
 // Robot lane: an env that just finished (or is parked waiting) looks at its next-scene slot. Returns 1 = install now.
-__device__ __forceinline__ int ar_decide(const StepArgs &A, int e, bool finished, bool parked)
+// `s` = the slot state read (volatile) earlier in this launch: a slot the generator publishes later is simply picked
+// up by the next step (the env parks for one step).
+__device__ __forceinline__ int ar_decide(const StepArgs &A, int e, uint8_t s, bool finished, bool parked)
 {
     if (!(finished || parked)) return 0;
-    const uint8_t s = *reinterpret_cast<volatile uint8_t *>(A.ar.n_state + e);
     if (s == CROWDSIM_SLOT_READY) return 1;
     A.st.active[e] = 0;                                        // park: nothing to install (yet)
     A.ar.want[e] = (s == CROWDSIM_SLOT_EXHAUSTED) ? 0 : 1;
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepA
                 }
             }
         }
-        if (A.has_ar) install = ar_decide(A, e, live && done, !live && A.ar.want[e] != 0);
+        if (A.has_ar) install = ar_decide(A, e, *reinterpret_cast<volatile uint8_t *>(A.ar.n_state + e), live && done, !live && A.ar.want[e] != 0);
     }
     if (A.has_ar) {
         if (is_robot) s.closest[le * L + N] = (double)install;     // the robot's own clearance slot is unused: env-wide flag

@@ -1,0 +1,172 @@
+"""Batched value-network robot policies on top of the fused lookahead kernel.
+
+The networks themselves stay plain PyTorch on the same device (north_star: "SARL's attention net stays PyTorch"); what
+is replaced is the reference's per-action Python loop (crowd_nav/policy/multi_human_rl.py:35-56, cadrl.py:156-170):
+81 x [env.onestep_lookahead (N ORCA solves each) + propagate + 5 tiny H2D copies + rotate + model(...).item()] per
+decision becomes ONE crowdsim_lookahead_pack launch (N ORCA solves per env, shared by all actions) + ONE batched
+forward over [B*81][N][13] + an argmax on device.
+
+Module / parameter names of the networks equal the reference's (sarl.py:9-65, cadrl.py:11-29), so reference
+checkpoints (rl_model.pth / il_model.pth state_dicts) load unchanged with load_state_dict().
+"""
+import itertools
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+
+def mlp(input_dim, mlp_dims, last_relu=False):
+    """cadrl.py:11-19"""
+    layers = []
+    dims = [input_dim] + list(mlp_dims)
+    for i in range(len(dims) - 1):
+        layers.append(nn.Linear(dims[i], dims[i + 1]))
+        if i != len(dims) - 2 or last_relu:
+            layers.append(nn.ReLU())
+    return nn.Sequential(*layers)
+
+
+def build_action_space(v_pref, speed_samples=5, rotation_samples=16, kinematics='holonomic'):
+    """cadrl.py:82-102 as an [A][2] float64 array: (0,0) first, then rotations x speeds (rotation-major)."""
+    holonomic = kinematics == 'holonomic'
+    speeds = [(np.exp((i + 1) / speed_samples) - 1) / (np.e - 1) * v_pref for i in range(speed_samples)]
+    if holonomic:
+        rotations = np.linspace(0, 2 * np.pi, rotation_samples, endpoint=False)
+    else:
+        rotations = np.linspace(-np.pi / 4, np.pi / 4, rotation_samples)
+    space = [(0.0, 0.0)]
+    for rotation, speed in itertools.product(rotations, speeds):
+        if holonomic:
+            space.append((speed * np.cos(rotation), speed * np.sin(rotation)))
+        else:
+            space.append((speed, rotation))
+    return np.array(space, dtype=np.float64)
+
+
+class CADRLValueNetwork(nn.Module):
+    """cadrl.py:22-29 (parameter prefix `value_network.`)."""
+
+    def __init__(self, input_dim=13, mlp_dims=(150, 100, 100, 1)):
+        super().__init__()
+        self.value_network = mlp(input_dim, mlp_dims)
+
+    def forward(self, state):
+        return self.value_network(state)
+
+
+class SARLValueNetwork(nn.Module):
+    """sarl.py:9-65. forward(state[batch][humans][13]) -> value[batch][1]. The reference copies the attention weights of
+    sample 0 to the host on every forward (sarl.py:54, visualisation only); here they stay on device in
+    `attention_weights` and are materialised on request."""
+
+    def __init__(self, input_dim=13, self_state_dim=6, mlp1_dims=(150, 100), mlp2_dims=(100, 50),
+                 mlp3_dims=(150, 100, 100, 1), attention_dims=(100, 100, 1), with_global_state=True):
+        super().__init__()
+        self.self_state_dim = self_state_dim
+        self.global_state_dim = mlp1_dims[-1]
+        self.mlp1 = mlp(input_dim, mlp1_dims, last_relu=True)
+        self.mlp2 = mlp(mlp1_dims[-1], mlp2_dims)
+        self.with_global_state = with_global_state
+        self.attention = mlp(mlp1_dims[-1] * 2 if with_global_state else mlp1_dims[-1], attention_dims)
+        self.mlp3 = mlp(mlp2_dims[-1] + self_state_dim, mlp3_dims)
+        self.attention_weights = None
+
+    def forward(self, state):
+        b, n, d = state.shape
+        self_state = state[:, 0, :self.self_state_dim]
+        h1 = self.mlp1(state.reshape(b * n, d))
+        h2 = self.mlp2(h1)
+        if self.with_global_state:
+            g = h1.view(b, n, -1).mean(dim=1, keepdim=True).expand(b, n, self.global_state_dim).reshape(b * n, -1)
+            att_in = torch.cat([h1, g], dim=1)
+        else:
+            att_in = h1
+        scores = self.attention(att_in).view(b, n)
+        scores_exp = torch.exp(scores) * (scores != 0).float()          # sarl.py:52 "masked softmax"
+        weights = (scores_exp / scores_exp.sum(dim=1, keepdim=True)).unsqueeze(2)
+        self.attention_weights = weights[0, :, 0].detach()
+        feat = (weights * h2.view(b, n, -1)).sum(dim=1)
+        return self.mlp3(torch.cat([self_state, feat], dim=1))
+
+
+class BatchedValuePolicy(object):
+    """Greedy one-step-lookahead policy over a value network (test / val phase of MultiHumanRL.predict and CADRL.predict).
+
+    act_batch(env) -> [B][2] float64 device tensor with, per env,
+        argmax_a  reward(s, a) + gamma ** (time_step * v_pref) * V(rotate(next_state(s, a)))       multi_human_rl.py:52
+    or the zero action when the robot already is within its radius of the goal (policy.py:41-48).
+    `joint` selects how humans enter the network: True = one [N][13] set per action (SARL, LSTM-RL, multi_human_rl.py:45),
+    False = CADRL's min over per-human values (cadrl.py:163-166)."""
+
+    name = 'BatchedValuePolicy'
+    kinematics = 'holonomic'
+    trainable = True
+    multiagent_training = True
+
+    def __init__(self, model, gamma=0.9, v_pref=1.0, time_step=0.25, joint=True, speed_samples=5, rotation_samples=16):
+        self.model = model
+        self.gamma = gamma
+        self.v_pref, self.time_step = v_pref, time_step
+        self.joint = joint
+        self.action_space_np = build_action_space(v_pref, speed_samples, rotation_samples)
+        self.actions = None
+        self.device = None
+        self.phase = 'test'
+        self.action_values = None
+        self._buf_states = None; self._buf_reward = None
+
+    def set_device(self, device):
+        self.device = torch.device(device)
+        self.model.to(self.device)
+        self.actions = torch.from_numpy(self.action_space_np).to(self.device)
+
+    def set_phase(self, phase):
+        self.phase = phase
+
+    def get_model(self):
+        return self.model
+
+    @torch.no_grad()
+    def act_batch(self, env):
+        if self.actions is None:
+            self.set_device(env.device)
+        A = self.actions.shape[0]
+        B, N = env.B, env.human_num
+        if self._buf_states is None or self._buf_states.shape[0] != B:
+            self._buf_states = torch.empty((B, A, N, 13), dtype=torch.float32, device=self.device)
+            self._buf_reward = torch.empty((B, A), dtype=torch.float64, device=self.device)
+        states, reward = env.lookahead_pack(self.actions, out_states=self._buf_states, out_reward=self._buf_reward)
+        discount = pow(self.gamma, self.time_step * self.v_pref)
+        if self.joint:
+            v = self.model(states.view(B * A, N, 13)).view(B, A)
+        else:
+            v = self.model(states.view(B * A * N, 13)).view(B, A, N).min(dim=2).values
+        values = reward + discount * v.double()                        # python-float arithmetic in the reference
+        self.action_values = values
+        best = values.argmax(dim=1)
+        act = self.actions[best]
+        s = env.state                                                  # policy.py:41-48 reach_destination
+        dy, dx = s.r_pos[:, 1] - s.r_goal[:, 1], s.r_pos[:, 0] - s.r_goal[:, 0]
+        reached = torch.sqrt(torch.addcmul(dy * dy, dx, dx)) < s.r_attr[:, 0]
+        return torch.where(reached.unsqueeze(1), torch.zeros_like(act), act)
+
+
+def make_sarl(gamma=0.9, v_pref=1.0, time_step=0.25, seed=None, **net_kw):
+    """SARL with the reference's default architecture (crowd_nav/configs/policy.config:43-50); random-init weights when
+    no checkpoint is loaded (there are no checkpoints in the reference repo)."""
+    if seed is not None:
+        torch.manual_seed(seed)
+    p = BatchedValuePolicy(SARLValueNetwork(**net_kw), gamma, v_pref, time_step, joint=True)
+    p.name = 'SARL'
+    return p
+
+
+def make_cadrl(gamma=0.9, v_pref=1.0, time_step=0.25, seed=None):
+    if seed is not None:
+        torch.manual_seed(seed)
+    p = BatchedValuePolicy(CADRLValueNetwork(), gamma, v_pref, time_step, joint=False)
+    p.name = 'CADRL'
+    p.multiagent_training = False
+    return p

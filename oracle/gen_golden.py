@@ -209,10 +209,16 @@ def run_rotate():
                     next_human_states, reward, done, info = env.onestep_lookahead(action)
                     batch = torch.cat([torch.Tensor([next_self_state + nhs]) for nhs in next_human_states], dim=0)
                     rot = policy.rotate(batch)
-                    per_action.append({'action': [R(action.vx), R(action.vy)], 'reward': R(reward),
+                    with torch.no_grad():
+                        value = policy.model(rot.unsqueeze(0)).data.item()
+                    per_action.append({'action': [R(action.vx), R(action.vy)], 'reward': R(reward), 'value': R(value),
                                        'rotated': [[R(v) for v in row] for row in rot.tolist()]})
                 cur = torch.cat([torch.Tensor([state.self_state + hs]) for hs in state.human_states], dim=0)
+                np_state = np.random.get_state()
+                chosen = policy.predict(state)                # the reference's own greedy decision (SARL, seed-0 weights)
+                np.random.set_state(np_state)
                 rows.append({'case': case, 'step': step, 'scene': scene(env), 'global_time': R(env.global_time),
+                             'sarl_action': [R(chosen.vx), R(chosen.vy)],
                              'rotated_current': [[R(v) for v in row] for row in policy.rotate(cur).tolist()],
                              'lookahead': per_action})
             # drive the robot with ORCA so the scene evolves through interesting states
@@ -222,11 +228,15 @@ def run_rotate():
                 break
     space = [[R(a.vx), R(a.vy)] for a in policy.action_space]
     with gzip.open(os.path.join(OUT, 'rotate_lookahead.json.gz'), 'wt') as f:
-        json.dump({'action_space': space, 'rows': rows}, f, separators=(',', ':'))
+        json.dump({'action_space': space, 'sarl_seed': 0, 'gamma': policy.gamma, 'rows': rows}, f, separators=(',', ':'))
     print('rotate/lookahead rows', len(rows))
 
 
 def main():
+    if '--rotate-only' in sys.argv:
+        os.makedirs(OUT, exist_ok=True)
+        run_rotate()
+        return
     quick = '--quick' in sys.argv
     os.makedirs(OUT, exist_ok=True)
     n = 50 if quick else 500

@@ -1,0 +1,73 @@
+"""GPU tests of the rollout layer: BatchedExplorer.run_k_episodes against the reference's own log lines, and the batched
+value-network policy (SARL) against the reference's greedy decisions."""
+import numpy as np
+import pytest
+import torch
+
+from util import SUITES, load_golden, fill_host_state
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('name,slots', [('circle5_invisible', 128), ('circle5_invisible', 500), ('square5_invisible', 64),
+                                        ('square20_invisible', 32), ('circle5_visible', 200)])
+def test_explorer_reproduces_reference_log_lines(cuda_env, name, slots):
+    """test.py --policy orca (crowd_nav/test.py:109): run_k_episodes(k, 'test', print_failure=True) over `slots` env
+    slots prints exactly the lines the reference printed for the same k cases (scenes generated on device)."""
+    from crowdnav_b200.explorer import BatchedExplorer
+    N, rule, vis, _ = SUITES[name]
+    d = load_golden('suite_' + name)
+    k = len(d['cases'])
+    env = cuda_env(slots, N, rule, robot_visible=bool(vis))
+    ex = BatchedExplorer(env, 'orca', gamma=0.9)
+    lines = []
+    import crowdnav_b200.explorer as E
+    stats = E.summarize.__wrapped__ if hasattr(E.summarize, '__wrapped__') else None
+    import logging
+    handler = logging.Handler(); handler.emit = lambda rec: lines.append(rec.getMessage())
+    root = logging.getLogger(); root.addHandler(handler); old = root.level; root.setLevel(logging.INFO)
+    try:
+        st = ex.run_k_episodes(k, 'test', print_failure=True)
+    finally:
+        root.removeHandler(handler); root.setLevel(old)
+    assert lines == d['log_lines']
+    assert st['env_steps'] == d['total_env_steps']
+    assert env.case_counter['test'] == k % env.case_size['test']
+
+
+def test_sarl_decisions_match_reference(cuda_env):
+    from crowdnav_b200.policy import make_sarl
+    d = load_golden('rotate_lookahead')
+    rows = d['rows']
+    import pyoracle
+    host = fill_host_state(pyoracle, [r['scene'] for r in rows], 5)
+    host.g_time[:] = [float(r['global_time']) for r in rows]
+    env = cuda_env(len(rows), 5, robot_policy='external_xy')
+    env.state.load_host(host)
+    pol = make_sarl(gamma=d['gamma'], seed=d['sarl_seed'])
+    pol.set_device(env.device)
+    act = pol.act_batch(env).cpu().numpy()
+    vals = pol.action_values.cpu().numpy()
+    disc = pow(d['gamma'], 0.25)
+    for e, r in enumerate(rows):
+        ref = np.array([float(la['reward']) + disc * float(la['value']) for la in r['lookahead']])
+        assert np.abs(vals[e] - ref).max() < 1e-4
+        top2 = np.sort(ref)[-2:]
+        if top2[1] - top2[0] > 1e-3:
+            assert [float(x) for x in r['sarl_action']] == [float(x) for x in act[e]], e
+
+
+def test_sarl_rollout_terminates_and_classifies(cuda_env):
+    """BASELINE config 3 shape (SARL rollout through run_k_episodes): random-init weights, every episode ends in one of
+    the three terminal classes, bookkeeping is consistent."""
+    from crowdnav_b200.explorer import BatchedExplorer
+    from crowdnav_b200.policy import make_sarl
+    env = cuda_env(256, 5)
+    pol = make_sarl(seed=0); pol.set_device(env.device)
+    ex = BatchedExplorer(env, pol, gamma=0.9)
+    st = ex.run_k_episodes(512, 'test')
+    assert st['success'] + st['collision'] + st['timeout'] == 512
+    rows = ex.last_rows.cpu().numpy()
+    assert set(np.unique(rows[:, 0]).astype(int)) <= {2, 3, 4}
+    assert (rows[:, 1] >= 1).all() and (rows[:, 1] <= 97).all()
+    assert (rows[rows[:, 0] == 4, 2] == 25.0).all()
