@@ -31,8 +31,8 @@ ALG_BYTES = lambda n: 8 * (19 + 12 * n) + 2      # 634 B at N=5,
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=600)
-    ap.add_argument('--warmup', type=int, default=100)
+    ap.add_argument('--steps', type=int, default=6400)
+    ap.add_argument('--warmup', type=int, default=640)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--envs', type=int, default=4096, help='envs per batch per GPU')
     ap.add_argument('--humans', type=int, default=5)

@@ -1,0 +1,169 @@
+"""CrowdSim: the reference's single-environment gym surface on top of the batched CUDA engine (B = 1).
+
+  configure / set_robot / reset / step / onestep_lookahead   crowd_sim/envs/crowd_sim.py:51-81, 251-315, 317-420
+  attributes read by callers: case_size, case_capacity, case_counter, time_limit, time_step, global_time, test_sim,
+  train_val_sim, human_num, humans, robot, states, human_times                                    (crowd_sim.py:24-49)
+
+One env.step = one crowdsim_step launch on a one-env batch + a device->host read of the few scalars the caller sees.
+The humans' ORCA solves, the collision / reward / terminal logic and the integration all run in the CUDA kernels; the
+Human / Robot objects are host mirrors refreshed after every call. No CPU fallback: without the CUDA library this
+raises. render() and get_human_times() are out of scope.
+"""
+import logging
+
+import numpy as np
+import torch
+
+from .. import _abi
+from ..batched import BatchedCrowdSim
+from .agents import Human
+from .statetypes import ActionRot, ActionXY, ObservableState, info_from_code
+
+
+class CrowdSim(object):
+    metadata = {'render.modes': ['human']}
+
+    def __init__(self):
+        self.time_limit = None; self.time_step = None
+        self.robot = None; self.humans = None
+        self.global_time = None; self.human_times = None
+        self.success_reward = None; self.collision_penalty = None
+        self.discomfort_dist = None; self.discomfort_penalty_factor = None
+        self.config = None
+        self.case_capacity = None; self.case_size = None; self.case_counter = None
+        self.randomize_attributes = None; self.train_val_sim = None; self.test_sim = None
+        self.square_width = None; self.circle_radius = None; self.human_num = None
+        self.states = None; self.action_values = None; self.attention_weights = None
+        self._engine = None
+
+    # ---- crowd_sim.py:51-79 ----
+    def configure(self, config):
+        self.config = config
+        eng = BatchedCrowdSim(1)
+        eng.configure(config)
+        self._engine = eng
+        for a in ('time_limit', 'time_step', 'randomize_attributes', 'success_reward', 'collision_penalty', 'discomfort_dist',
+                  'discomfort_penalty_factor', 'case_capacity', 'case_size', 'train_val_sim', 'test_sim', 'square_width',
+                  'circle_radius', 'human_num', 'case_counter'):
+            setattr(self, a, getattr(eng, a))
+        logging.info('human number: {}'.format(self.human_num))
+        logging.info("Randomize human's radius and preferred speed" if self.randomize_attributes
+                     else "Not randomize human's radius and preferred speed")
+        logging.info('Training simulation: {}, test simulation: {}'.format(self.train_val_sim, self.test_sim))
+        logging.info('Square width: {}, circle width: {}'.format(self.square_width, self.circle_radius))
+
+    def set_robot(self, robot):
+        self.robot = robot
+
+    def _sync_engine_config(self):
+        eng, r = self._engine, self.robot
+        eng.robot_visible = bool(r.visible); eng.robot_radius = r.radius; eng.robot_v_pref = r.v_pref
+        eng.test_sim, eng.train_val_sim = self.test_sim, self.train_val_sim
+        eng.randomize_attributes = self.randomize_attributes
+        eng.set_robot_policy('external_rot' if r.kinematics == 'unicycle' else 'external_xy')
+
+    def _pull(self):
+        """Refresh the host mirrors from the device state."""
+        s = self._engine.state
+        hp, hv, hg, ha = (t[0].tolist() for t in (s.h_pos, s.h_vel, s.h_goal, s.h_attr))
+        for i, h in enumerate(self.humans):
+            h.px, h.py = hp[i]; h.vx, h.vy = hv[i]; h.gx, h.gy = hg[i]; h.radius, h.v_pref = ha[i]
+        r = self.robot
+        (r.px, r.py), (r.vx, r.vy), (r.gx, r.gy) = s.r_pos[0].tolist(), s.r_vel[0].tolist(), s.r_goal[0].tolist()
+        r.theta = float(s.r_theta[0])
+        self.global_time = float(s.g_time[0])
+
+    # ---- crowd_sim.py:251-312 ----
+    def reset(self, phase='test', test_case=None):
+        if self.robot is None:
+            raise AttributeError('robot has to be set!')
+        assert phase in ['train', 'val', 'test']
+        if test_case is not None:
+            self.case_counter[phase] = test_case
+        multi = getattr(self.robot.policy, 'multiagent_training', True)
+        if not multi and phase in ('train', 'val'):
+            raise NotImplementedError('single-human training scenes (crowd_sim.py:265-267,278) are not built yet')
+        if not multi:
+            self.train_val_sim = 'circle_crossing'
+        self._sync_engine_config()
+        eng = self._engine
+        case = self.case_counter[phase]
+        if case >= 0:
+            eng.reset(phase, cases=[case])
+            self.case_counter[phase] = (case + 1) % self.case_size[phase]
+            n = self.human_num
+        else:
+            assert phase == 'test'
+            if case != -1:
+                raise NotImplementedError
+            n = 3                                             # crowd_sim.py:286-292 hand-placed debug scene
+            if eng.human_num != 3:
+                eng.human_num = 3; eng._alloc()
+            s = eng.state
+            s.h_pos.copy_(torch.tensor([[[0., -6.], [-5., -5.], [5., -5.]]], dtype=torch.float64))
+            s.h_goal.copy_(torch.tensor([[[0., 5.], [-5., 5.], [5., 5.]]], dtype=torch.float64))
+            s.h_vel.zero_(); s.h_attr[..., 0] = eng.human_radius; s.h_attr[..., 1] = eng.human_v_pref
+            s.r_pos.copy_(torch.tensor([[0., -self.circle_radius]], dtype=torch.float64)); s.r_goal.copy_(torch.tensor([[0., self.circle_radius]], dtype=torch.float64))
+            s.r_vel.zero_(); s.r_attr.copy_(torch.tensor([[eng.robot_radius, eng.robot_v_pref]], dtype=torch.float64))
+            s.r_theta.fill_(np.pi / 2); s.g_time.zero_(); s.active.fill_(1)
+            self.human_num = 3
+        self.humans = [Human(self.config, 'humans') for _ in range(n)]
+        self.human_times = [0] * n
+        self._pull()
+        for h in self.humans:
+            h.theta = 0 if case >= 0 else np.pi / 2
+        for agent in [self.robot] + self.humans:
+            agent.time_step = self.time_step
+            if agent.policy is not None:
+                agent.policy.time_step = self.time_step
+        self.states = list()
+        if hasattr(self.robot.policy, 'action_values'):
+            self.action_values = list()
+        if hasattr(self.robot.policy, 'get_attention_weights'):
+            self.attention_weights = list()
+        if self.robot.sensor != 'coordinates':
+            raise NotImplementedError
+        return [h.get_observable_state() for h in self.humans]
+
+    def onestep_lookahead(self, action):
+        return self.step(action, update=False)
+
+    # ---- crowd_sim.py:317-420 ----
+    def step(self, action, update=True):
+        eng = self._engine
+        if isinstance(action, ActionRot):
+            act = torch.tensor([[action.v, action.r]], dtype=torch.float64)
+        else:
+            act = torch.tensor([[action.vx, action.vy]], dtype=torch.float64)
+        s = eng.state
+        snap = None
+        if not update:                                         # nothing may be mutated (crowd_sim.py:414-416)
+            snap = [getattr(s, f).clone() for f in s.FIELDS] + [s.active.clone()]
+        else:
+            self.states.append([self.robot.get_full_state(), [h.get_full_state() for h in self.humans]])
+            if hasattr(self.robot.policy, 'action_values'):
+                self.action_values.append(self.robot.policy.action_values)
+            if hasattr(self.robot.policy, 'get_attention_weights'):
+                self.attention_weights.append(self.robot.policy.get_attention_weights())
+        eng.step(act.to(eng.device))
+        reward = float(eng.reward[0]); done = bool(eng.done[0]); code = int(eng.info[0])
+        info = info_from_code(code, float(eng.dmin[0]))
+        if update:
+            self._pull()
+            for i, h in enumerate(self.humans):
+                if self.human_times[i] == 0 and h.reached_destination():
+                    self.human_times[i] = self.global_time
+            ob = [h.get_observable_state() for h in self.humans]
+        else:
+            hp, hv = s.h_pos[0].tolist(), s.h_vel[0].tolist()
+            ob = [ObservableState(hp[i][0], hp[i][1], hv[i][0], hv[i][1], h.radius) for i, h in enumerate(self.humans)]
+            for f, t in zip(s.FIELDS, snap[:-1]):
+                getattr(s, f).copy_(t)
+            s.active.copy_(snap[-1])
+        return ob, reward, done, info
+
+    def render(self, mode='human', output_file=None):
+        raise NotImplementedError('rendering is out of scope of the CUDA path (SURVEY.md 2b)')
+
+    def get_human_times(self):
+        raise NotImplementedError('centralised multi-step ORCA (crowd_sim.py:209-249) is a next row (SURVEY.md 8f row 4)')

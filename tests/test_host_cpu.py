@@ -113,3 +113,28 @@ def test_sarl_state_dict_keys_match_reference_layout():
     assert SARLValueNetwork().mlp1[0].in_features == 13 and SARLValueNetwork().attention[0].in_features == 200
     assert SARLValueNetwork().mlp3[0].in_features == 56
     assert 'value_network.0.weight' in CADRLValueNetwork().state_dict()
+
+
+def test_compat_types_and_module_aliases():
+    """crowdnav_b200.compat.install(): the reference's import paths resolve; value types keep the reference's contract."""
+    import crowdnav_b200.compat as compat
+    compat.install(force_gym_shim=True)
+    import gym
+    from crowd_sim.envs.utils.state import FullState, ObservableState, JointState
+    from crowd_sim.envs.utils.action import ActionXY, ActionRot
+    from crowd_sim.envs.utils.info import Timeout, ReachGoal, Danger, Collision, Nothing
+    from crowd_sim.envs.policy.policy_factory import policy_factory
+    from crowd_sim.envs.utils.robot import Robot  # noqa: F401
+    from crowd_nav.utils.explorer import Explorer, average  # noqa: F401
+    fs = FullState(1, 2, 3, 4, 0.3, 5, 6, 1.0, 0.5); ob = ObservableState(7, 8, 9, 10, 0.4)
+    assert fs + ob == (1, 2, 3, 4, 0.3, 5, 6, 1.0, 0.5, 7, 8, 9, 10, 0.4)          # state.py:17-18,36-37 -> the 14-tuple
+    assert not isinstance(fs, ObservableState) and fs.position == (1, 2) and fs.goal_position == (5, 6) and ob.velocity == (9, 10)
+    JointState(fs, [ob])
+    with pytest.raises(AssertionError):
+        JointState(ob, [ob])
+    assert (str(Timeout()), str(ReachGoal()), str(Danger(0.1)), str(Collision()), str(Nothing())) == \
+        ('Timeout', 'Reaching goal', 'Too close', 'Collision', '')
+    assert Danger(0.05).min_dist == 0.05 and ActionXY(1, 2).vx == 1 and ActionRot(1, 2).r == 2
+    assert set(policy_factory) == {'linear', 'orca', 'none'} and policy_factory['none']() is None
+    assert average([]) == 0 and average([1, 2]) == 1.5
+    assert type(gym.make('CrowdSim-v0')).__name__ == 'CrowdSim'
