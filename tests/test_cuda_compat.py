@@ -30,11 +30,11 @@ def _make(human_num=5, test_sim='circle_crossing', robot_visible=False):
 
 
 def test_reference_test_py_flow_reproduces_first_cases():
-    from crowd_nav.utils.explorer import Explorer
     from crowdnav_b200.explorer import summarize
     d = load_golden('suite_circle5_invisible')
     k = 16
     env, robot = _make()
+    from crowd_nav.utils.explorer import Explorer
     explorer = Explorer(env, robot, torch.device('cuda:0'), gamma=0.9)
     lines = []
     handler = logging.Handler(); handler.emit = lambda rec: lines.append(rec.getMessage())
@@ -52,10 +52,9 @@ def test_reference_test_py_flow_reproduces_first_cases():
 
 
 def test_step_and_lookahead_semantics():
-    from crowd_sim.envs.utils.action import ActionXY
-    from crowd_sim.envs.utils.info import Danger, Nothing, Collision, ReachGoal, Timeout
     d = load_golden('traj_circle5_invisible')['trajectories']['3']
     env, robot = _make()
+    from crowd_sim.envs.utils.info import Danger, Nothing, Collision, ReachGoal, Timeout
     ob = env.reset('test', 3)
     r0, h0 = scene_arrays(d[0]['pre'])
     assert abs(env.humans[0].px - h0[0, 0]) < 1e-12 and len(ob) == 5 and env.global_time == 0
