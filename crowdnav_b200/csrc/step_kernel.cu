@@ -219,16 +219,14 @@ static int flat_snap_epw(int N, int epw)
     return best;
 }
 
-// Heuristic packing: aim for >= ~6 resident warps per SM sub-partition before packing envs more densely.
-// (148 SMs x 4 sub-partitions; tuned on B200 with scripts/tune_epw.py, see DESIGN.md.)
+// Packing of the small-crowd kernel: dense (32 / (N + 1) envs per warp). Sparser packings (fewer envs per warp, in-place
+// lp3) give more, less divergent warps, but were measured on B200 at 1 k .. 1 M envs and are never faster: the kernel's
+// instruction stream is almost data-independent, so sparse warps only multiply the instruction count
+// (scripts/tune_epw.py, profiles/r01_tune_epw_n5.txt). crowdsim_debug_force_epw() keeps the knob for re-tuning.
 static int flat_pick_epw(int B, int N)
 {
-    const int dense = 32 / (N + 1);
-    const long target_warps = 148L * 4 * 6;
-    long epw = (B + target_warps - 1) / target_warps;
-    if (epw < 1) epw = 1;
-    if (epw > dense) epw = dense;
-    return (int)epw;
+    (void)B;
+    return 32 / (N + 1);
 }
 
 static int launch(const crowdsim_params *prm, int B, int N, const crowdsim_state *st, const crowdsim_step_io *io,

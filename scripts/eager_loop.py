@@ -1,0 +1,21 @@
+#!/usr/bin/env python
+"""The bench's step / scene-prefetch sequence with EAGER launches (no CUDA graph), for ncu: same kernels, same arguments,
+same rotating batches as bench.py's timed region; ncu serialises launches anyway, so compare SHARES, not absolutes."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from crowdnav_b200.batched import BatchedCrowdSim, default_config
+
+B, N, pools, K = 4096, 5, 64, 400
+envs = []
+for p in range(pools):
+    env = BatchedCrowdSim(B); env.configure(default_config(human_num=N)); env.set_robot_policy('orca')
+    env.k_total = 8 * B
+    env.track_episodes(env.k_total, gamma=0.9); env.set_case_queue(p * env.k_total, env.k_total, 'train')
+    env.enable_autoreset('circle_crossing'); env.reset_seeds(use_queue=True); env.prefetch(); envs.append(env)
+torch.cuda.synchronize()
+for t in range(K):
+    env = envs[t % pools]
+    env.step(); env.prefetch()
+torch.cuda.synchronize()
+print('done', K)
