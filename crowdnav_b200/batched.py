@@ -340,14 +340,19 @@ class HostStepper(object):
         def body():
             self.d_action.copy_(self.h_action, non_blocking=True)
             env.step(self.d_action)                    # installs prefetched scenes of finished envs when auto-reset is on
-            if env.autoreset is not None:
-                env.prefetch()
+            if env.autoreset is not None:              # refill consumed slots on a side branch of the graph
+                self.side.wait_stream(self.stream)
+                with torch.cuda.stream(self.side):
+                    env.prefetch()
             if next_orca_action:
                 env.orca_act(self.d_next)
                 self.h_next_action.copy_(self.d_next, non_blocking=True)
             self.h_pos.copy_(env.state.h_pos, non_blocking=True); self.h_vel.copy_(env.state.h_vel, non_blocking=True)
             self.h_reward.copy_(env.reward, non_blocking=True); self.h_done.copy_(env.done, non_blocking=True)
             self.h_info.copy_(env.info, non_blocking=True)
+            if env.autoreset is not None:
+                self.stream.wait_stream(self.side)     # join: the refill must be complete before the next step
+        self.side = torch.cuda.Stream(device=dev)
         with torch.cuda.stream(self.stream):
             body()                                     # warm-up outside capture (lazy inits)
         self.stream.synchronize()

@@ -257,7 +257,7 @@ static int launch(const crowdsim_params *prm, int B, int N, const crowdsim_state
     if (A.has_ep) A.ep = *ep; else memset(&A.ep, 0, sizeof(A.ep));
     A.has_ar = (ar != nullptr && !act_only);
     if (A.has_ar) A.ar = *ar; else memset(&A.ar, 0, sizeof(A.ar));
-    if (!act_only && N >= 1 && N <= 5 && !g_force_generic) {
+    if (N >= 1 && N <= 5 && !g_force_generic) {
         // small crowds: register-resident solver, whole envs per warp (step_flat.cuh). Packing: dense when the batch
         // fills the chip, sparse (fewer envs per warp, in-place lp3) when it does not -- see flat_pick_epw().
         const int epw = flat_snap_epw(N, g_force_epw > 0 ? g_force_epw : flat_pick_epw(B, N));

@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""Secondary measurements for DESIGN.md (run under gpurun): BASELINE configs 1, 3 and 4 on one GPU."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from crowdnav_b200.batched import BatchedCrowdSim, default_config
+from crowdnav_b200.explorer import BatchedExplorer
+from crowdnav_b200.policy import make_sarl
+
+out = {}
+
+
+def graph_time(fn, S=20, reps=5):
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(S):
+            fn()
+    g.replay(); torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / S)
+    return best * 1e3
+
+
+# config 4: 4096 envs x 20 humans, square crossing (generic kernel)
+for B in (4096, 65536):
+    env = BatchedCrowdSim(B); env.configure(default_config(human_num=20, test_sim='square_crossing', train_val_sim='square_crossing'))
+    env.set_robot_policy('orca'); env.reset_seeds(torch.arange(B) + 2000, rule='square_crossing')
+    for _ in range(5): env.step()
+    us = graph_time(env.step)
+    out['cfg4_step_N20_B%d' % B] = {'us_per_launch': round(us, 2), 'env_steps_per_s': round(B / us * 1e6), 'GBps': round(B * 2074 / us / 1e3, 1)}
+    del env
+
+# config 3: SARL rollout pieces at 4096 envs x 5 humans
+B = 4096
+env = BatchedCrowdSim(B); env.configure(default_config(human_num=5)); env.set_robot_policy('external_xy')
+env.reset_seeds(torch.arange(B) + 2000)
+pol = make_sarl(seed=0); pol.set_device(env.device)
+for _ in range(3): a = pol.act_batch(env)
+st = torch.empty((B, 81, 5, 13), dtype=torch.float32, device=env.device); rw = torch.empty((B, 81), dtype=torch.float64, device=env.device)
+us_look = graph_time(lambda: env.lookahead_pack(pol.actions, out_states=st, out_reward=rw), S=10)
+out['cfg3_lookahead_pack'] = {'us_per_launch': round(us_look, 1), 'written_GBps': round(B * 81 * (5 * 13 * 4 + 8) / us_look / 1e3, 1)}
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(20): a = pol.act_batch(env)
+torch.cuda.synchronize(); out['cfg3_sarl_decision_ms'] = round((time.perf_counter() - t0) / 20 * 1e3, 3)
+ex = BatchedExplorer(env, pol, gamma=0.9)
+torch.cuda.synchronize(); t0 = time.perf_counter()
+stats = ex.run_k_episodes(4096, 'train')
+torch.cuda.synchronize(); dt = time.perf_counter() - t0
+out['cfg3_sarl_rollout'] = {'episodes': 4096, 'env_steps': stats['env_steps'], 'seconds': round(dt, 3), 'env_steps_per_s': round(stats['env_steps'] / dt),
+                            'rates': [stats['success_rate'], stats['collision_rate'], stats['timeout_rate']]}
+
+# config 1 on the GPU: the 500 test cases with the ORCA robot, wall clock of run_k_episodes (includes host loop + sync)
+env = BatchedCrowdSim(512); env.configure(default_config(human_num=5))
+ex = BatchedExplorer(env, 'orca', gamma=0.9)
+ex.run_k_episodes(500, 'test'); env.case_counter['test'] = 0
+torch.cuda.synchronize(); t0 = time.perf_counter()
+stats = ex.run_k_episodes(500, 'test')
+torch.cuda.synchronize(); dt = time.perf_counter() - t0
+out['cfg1_500_test_cases'] = {'seconds': round(dt, 4), 'env_steps': stats['env_steps'], 'success': stats['success'], 'collision': stats['collision'], 'timeout': stats['timeout']}
+print(json.dumps(out, indent=1))
