@@ -85,7 +85,7 @@ def declare(lib, prefix='crowdsim_', with_stream=True):
     return lib
 
 
-EXPORTS = ('crowdsim_abi_version', 'crowdsim_device_check', 'crowdsim_launch_count', 'crowdsim_debug_force_generic', 'crowdsim_debug_force_epw', 'crowdsim_step',
+EXPORTS = ('crowdsim_abi_version', 'crowdsim_device_check', 'crowdsim_launch_count', 'crowdsim_debug_force_generic', 'crowdsim_step',
            'crowdsim_orca_act', 'crowdsim_reset', 'crowdsim_prefetch_scenes', 'crowdsim_pack_joint', 'crowdsim_lookahead_pack')
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc', 'libcrowdsim_b200.so')
@@ -111,8 +111,6 @@ def load():
         lib.crowdsim_launch_count.restype = C.c_ulonglong
         lib.crowdsim_debug_force_generic.argtypes = [C.c_int]
         lib.crowdsim_debug_force_generic.restype = None
-        lib.crowdsim_debug_force_epw.argtypes = [C.c_int]
-        lib.crowdsim_debug_force_epw.restype = None
         declare(lib)
         if lib.crowdsim_abi_version() != ABI_VERSION:
             raise CudaLibraryMissing('ABI version mismatch: library %d, python %d'

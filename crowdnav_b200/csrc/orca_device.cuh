@@ -148,6 +148,38 @@ __device__ __forceinline__ int lp2(const Lines &L, int n, float radius, V2 opt, 
     return n;
 }
 
+// Projected lines of line i onto lines j < i (the loop body of linearProgram3): written to P in j order, parallel
+// same-direction lines skipped. Returns their number.
+__device__ __forceinline__ int lp3_project(const Lines &L, int i, const Lines &P)
+{
+    const V2 li_p = L.point(i), li_d = L.dir(i);
+    int np = 0;
+    for (int j = 0; j < i; ++j) {
+        const V2 lj_p = L.point(j), lj_d = L.dir(j);
+        V2 pp;
+        const float d = det(li_d, lj_d);
+        if (fabsf(d) <= kEps) {
+            if (dot(li_d, lj_d) > 0.0f) continue;
+            pp = 0.5f * (li_p + lj_p);
+        } else {
+            const float t = det(lj_d, li_p - lj_p) / d;
+            pp = li_p + t * li_d;
+        }
+        P.set(np++, pp, normalize(lj_d - li_d));
+    }
+    return np;
+}
+
+// The sub-problem of line i inside linearProgram3: linearProgram2 over the projected lines, direction optimisation,
+// STARTING FROM optVelocity * radius -- it does not depend on the running result, only on the lines. Returns false if
+// it fails (RVO2 then keeps the current result).
+__device__ __forceinline__ bool lp3_subproblem(const Lines &L, int i, float radius, const Lines &P, V2 &r2)
+{
+    const V2 li_d = L.dir(i);
+    const int np = lp3_project(L, i, P);
+    return !(lp2(P, np, radius, mk(-li_d.y, li_d.x), true, r2) < np);
+}
+
 // A.4 lp3 (numObstLines == 0: crowd_sim never adds obstacles)
 static __device__ __noinline__ void lp3(const Lines &L, int n, int begin, float radius, const Lines &P, V2 &result)
 {
@@ -155,22 +187,8 @@ static __device__ __noinline__ void lp3(const Lines &L, int n, int begin, float 
     for (int i = begin; i < n; ++i) {
         const V2 li_p = L.point(i), li_d = L.dir(i);
         if (det(li_d, li_p - result) > distance) {
-            int np = 0;
-            for (int j = 0; j < i; ++j) {
-                const V2 lj_p = L.point(j), lj_d = L.dir(j);
-                V2 pp;
-                const float d = det(li_d, lj_d);
-                if (fabsf(d) <= kEps) {
-                    if (dot(li_d, lj_d) > 0.0f) continue;
-                    pp = 0.5f * (li_p + lj_p);
-                } else {
-                    const float t = det(lj_d, li_p - lj_p) / d;
-                    pp = li_p + t * li_d;
-                }
-                P.set(np++, pp, normalize(lj_d - li_d));
-            }
-            const V2 tmp = result;
-            if (lp2(P, np, radius, mk(-li_d.y, li_d.x), true, result) < np) result = tmp;
+            V2 r2 = result;
+            if (lp3_subproblem(L, i, radius, P, r2)) result = r2;      // on failure the current result is kept
             distance = det(li_d, li_p - result);
         }
     }

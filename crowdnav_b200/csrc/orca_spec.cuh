@@ -16,8 +16,8 @@
 // sequential code (parity tests compare every velocity for equality), while a warp of 32 different solves executes
 // one common instruction stream with M(M-1)/2 independent divisions in flight instead of the union of 32 divergent
 // control paths.
-// The same holds for linearProgram3: the projected lines of (i, j) depend only on the lines, and the lp1 candidates of
-// the projected problems depend only on those; only two short scans are sequential.
+// linearProgram3 has a similar structure one level up (its per-line sub-problems do not depend on the running result);
+// step_flat.cuh exploits that by running the sub-problems of a queued solve on parallel lanes.
 #pragma once
 #include "orca_device.cuh"
 
@@ -128,53 +128,6 @@ __device__ __forceinline__ V2 lp2_init(V2 opt, float radius)
 {
     if (abssq(opt) > sqr(radius)) { const V2 nv = normalize(opt); return mk(nv.x * radius, nv.y * radius); }
     return opt;
-}
-
-// One outer iteration (line I) of linearProgram3: projected lines of (I, j < I), their lp1 candidates, then the scan.
-template <int M, int I>
-__device__ __forceinline__ void lp3_iter(const RegLines<M> &R, int n, int begin, float radius, V2 &result, float &distance)
-{
-    RegLines<M> P; bool pv[M];
-    const V2 oi = mk(-R.d[I].y, R.d[I].x);
-    #pragma unroll
-    for (int j = 0; j < M; ++j) { pv[j] = false; P.p[j] = mk(0.f, 0.f); P.d[j] = mk(0.f, 0.f); }
-    #pragma unroll
-    for (int j = 0; j < I; ++j) {
-        const float d = det(R.d[I], R.d[j]);
-        const bool par = fabsf(d) <= kEps;
-        const float t = det(R.d[j], R.p[I] - R.p[j]) / d;
-        const V2 pp_par = 0.5f * (R.p[I] + R.p[j]);
-        const V2 pp_gen = R.p[I] + t * R.d[I];
-        pv[j] = !(par && dot(R.d[I], R.d[j]) > 0.0f);
-        P.p[j] = par ? pp_par : pp_gen;
-        P.d[j] = normalize(R.d[j] - R.d[I]);
-    }
-    V2 pc[M]; bool pf[M];
-    lp1_all<M, I>(P, pv, radius, oi, true, pc, pf);
-    const bool viol = (I >= begin) && (I < n) && det(R.d[I], R.p[I] - result) > distance;
-    if (viol) {
-        V2 r2;
-        const int f = lp2_scan<M, I>(P, pv, I, pc, pf, mk(oi.x * radius, oi.y * radius), r2);
-        if (!(f < I)) result = r2;                 // failure keeps the current result (tempResult)
-        distance = det(R.d[I], R.p[I] - result);
-    }
-}
-
-// linearProgram3 (numObstLines == 0), speculative: per line the projected problem is built and solved branch-free.
-template <int M>
-__device__ __forceinline__ void lp3_spec(const RegLines<M> &R, int n, int begin, float radius, V2 &result)
-{
-    float distance = 0.0f;
-    // i == 0: no projected lines; linearProgram2 over an empty set returns optVelocity * radius
-    if (begin == 0 && n > 0 && det(R.d[0], R.p[0] - result) > 0.0f) {
-        result = mk(-R.d[0].y * radius, R.d[0].x * radius);
-        distance = det(R.d[0], R.p[0] - result);
-    }
-    if constexpr (M > 1) lp3_iter<M, 1>(R, n, begin, radius, result, distance);
-    if constexpr (M > 2) lp3_iter<M, 2>(R, n, begin, radius, result, distance);
-    if constexpr (M > 3) lp3_iter<M, 3>(R, n, begin, radius, result, distance);
-    if constexpr (M > 4) lp3_iter<M, 4>(R, n, begin, radius, result, distance);
-    static_assert(M <= 5, "lp3_spec is instantiated for at most 5 lines");
 }
 
 }  // namespace orca

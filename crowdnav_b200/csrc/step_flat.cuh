@@ -9,8 +9,11 @@
 // the LP code has static register indexing, no local/shared memory traffic and instruction-level parallelism
 // across the independent (i, j) line pairs.
 // linearProgram3 (needed by ~4.6 % of the solves, i.e. by some lane of ~3 of 4 warps) is NOT run in place: the
-// solves that need it are compacted into a block-level shared-memory queue and processed densely by the first
-// warp(s) of the block, so the expensive fallback is paid by few lanes instead of being serialised into every warp.
+// solves that need it are compacted into a block-level shared-memory queue. Inside linearProgram3 the sub-problem of
+// each line i (linearProgram2 over the lines projected onto i, started from optVelocity * radius) depends only on the
+// lines, not on the running result, so the <= N-1 sub-problems of a queued solve run on N-1 LANES IN PARALLEL (the
+// sequential shared-memory LP code of orca_device.cuh), followed by a 4-step scan. Before this, the pass was a
+// ~1500-instruction serial chain on a handful of lanes with the whole block waiting: ~4.5 of 14 us per launch.
 //
 // Evidence that motivated this design (profiles/r01_*): one-thread-per-agent with shared-memory lines ran at 13.6/32
 // active lanes and 3480 instructions per warp; the warp-per-env cooperative variant needed 1750 warp instructions
@@ -23,21 +26,20 @@ namespace cs {
 
 #define CS_FULL 0xffffffffu
 
-// EPW = whole envs packed per warp (1 .. 32/L). Dense packing (EPW = 32/L) minimises instructions per env-step and is
-// right when the batch fills the chip; sparse packing (fewer envs per warp, the other lanes idle) gives more,
-// less divergent warps and is faster when the batch is too small to hide latency (4096 envs = 0.8 dense warps per
-// SM sub-partition). COMPACT selects the block-compacted lp3 pass (pays two block barriers) over running lp3 in place.
-// STAGE is a profiling aid (scripts/latency_probe.cu instantiates cut-down variants to attribute latency); the library
-// only instantiates the full kernel (STAGE = 99).
-template <int N, int EPW, bool COMPACT, int STAGE = 99>
+// EPW = 32 / (N + 1) whole envs per warp (dense packing; sparser packings were measured and are never faster, see
+// step_kernel.cu: flat_pick_epw). STAGE is a profiling aid (scripts/latency_probe.cu instantiates cut-down variants to
+// attribute latency); the library only instantiates the full kernel (STAGE = 99).
+template <int N, int STAGE = 99>
 __global__ void __launch_bounds__(128) step_flat_kernel(const __grid_constant__ StepArgs A)
 {
     if constexpr (STAGE == 0) return;
     using namespace orca;
-    constexpr int L = N + 1, M = N, WPB = 4, T = 32 * WPB;
-    static_assert(EPW >= 1 && EPW * L <= 32, "envs per warp");
-    constexpr int QF = COMPACT ? 4 * M + 5 : 1;             // floats per queued lp3 work item
-    __shared__ float s_q[QF][T];                            // [field][slot]: conflict-free for consecutive slots
+    constexpr int L = N + 1, M = N, EPW = 32 / L, WPB = 4, T = 32 * WPB;
+    constexpr int SUB = (M > 1) ? M - 1 : 1;                // lanes per queued lp3 item (sub-problems i = 1 .. M-1)
+    constexpr int QF = 4 * M + 5;                           // floats per queued lp3 work item
+    __shared__ float s_q[QF][T];                            // [field][slot]: lines of an item = orca::Lines(base = &s_q[0][slot], stride = T)
+    __shared__ float s_p[4 * SUB][T];                       // per-thread projected lines of the sub-problem
+    __shared__ float s_r2[3][T];                            // per-thread sub-problem result (x, y, ok)
     __shared__ float s_res[2][T];
     __shared__ int s_qcount;
 
@@ -48,7 +50,7 @@ __global__ void __launch_bounds__(128) step_flat_kernel(const __grid_constant__ 
     const int e = (blockIdx.x * WPB + wib) * EPW + le;
     const bool is_robot = (a == N);
     const bool env_ok = (le < EPW) && (e < A.B);
-    if (COMPACT && tid == 0) s_qcount = 0;
+    if (tid == 0) s_qcount = 0;
 
     // ---- all global loads of the step are issued up front, unconditionally for valid envs, so that they overlap into ONE
     // DRAM round trip (active flag -> state -> episode accumulators / slot state used to be dependent ones) ----
@@ -152,36 +154,60 @@ __global__ void __launch_bounds__(128) step_flat_kernel(const __grid_constant__ 
         return;
     }
     const bool need3 = solves && fail < nl;
-    if constexpr (!COMPACT) {
-        if (need3) lp3_spec<M>(R, nl, fail, max_speed, nv);
-    } else {
-        __syncthreads();                                     // s_qcount = 0 visible
-        int slot = -1;
-        if (need3) {
-            slot = atomicAdd(&s_qcount, 1);
-            #pragma unroll
-            for (int kk = 0; kk < M; ++kk) {
-                s_q[4 * kk + 0][slot] = R.p[kk].x; s_q[4 * kk + 1][slot] = R.p[kk].y;
-                s_q[4 * kk + 2][slot] = R.d[kk].x; s_q[4 * kk + 3][slot] = R.d[kk].y;
-            }
-            s_q[4 * M + 0][slot] = __int_as_float(nl); s_q[4 * M + 1][slot] = __int_as_float(fail);
-            s_q[4 * M + 2][slot] = max_speed; s_q[4 * M + 3][slot] = nv.x; s_q[4 * M + 4][slot] = nv.y;
+    __syncthreads();                                         // s_qcount = 0 visible
+    int slot = -1;
+    if (need3) {
+        slot = atomicAdd(&s_qcount, 1);
+        #pragma unroll
+        for (int kk = 0; kk < M; ++kk) {
+            s_q[4 * kk + 0][slot] = R.p[kk].x; s_q[4 * kk + 1][slot] = R.p[kk].y;
+            s_q[4 * kk + 2][slot] = R.d[kk].x; s_q[4 * kk + 3][slot] = R.d[kk].y;
         }
-        if (__syncthreads_or(need3 ? 1 : 0)) {
-            const int cnt = s_qcount;
-            if (tid < cnt) {                                 // dense: work item q is handled by thread q
-                RegLines<M> Q;
-                #pragma unroll
-                for (int kk = 0; kk < M; ++kk) { Q.p[kk] = mk(s_q[4 * kk + 0][tid], s_q[4 * kk + 1][tid]); Q.d[kk] = mk(s_q[4 * kk + 2][tid], s_q[4 * kk + 3][tid]); }
-                const int qn = __float_as_int(s_q[4 * M + 0][tid]), qf = __float_as_int(s_q[4 * M + 1][tid]);
-                const float qr = s_q[4 * M + 2][tid];
-                V2 res = mk(s_q[4 * M + 3][tid], s_q[4 * M + 4][tid]);
-                lp3_spec<M>(Q, qn, qf, qr, res);
-                s_res[0][tid] = res.x; s_res[1][tid] = res.y;
+        s_q[4 * M + 0][slot] = __int_as_float(nl); s_q[4 * M + 1][slot] = __int_as_float(fail);
+        s_q[4 * M + 2][slot] = max_speed; s_q[4 * M + 3][slot] = nv.x; s_q[4 * M + 4][slot] = nv.y;
+    }
+    if (__syncthreads_or(need3 ? 1 : 0)) {
+        const int cnt = s_qcount;
+        constexpr int IPP = T / SUB;                         // items per pass
+        for (int base = 0; base < cnt; base += IPP) {
+            const int item = base + tid / SUB, i = tid % SUB + 1;
+            const bool mine = (tid < IPP * SUB) && item < cnt;
+            if (mine) {
+                const Lines Lq = { &s_q[0][item], T };
+                const int qn = __float_as_int(s_q[4 * M + 0][item]);
+                bool ok = false; V2 r2 = mk(0.f, 0.f);
+                if (M > 1 && i < qn) {
+                    // sequential shared-memory LP code (early exits): measured faster here than a register-resident
+                    // speculative version of the sub-problem (LP3 stage 3.5 vs 4.5 us at 4096 envs)
+                    const Lines Pq = { &s_p[0][tid], T };
+                    ok = lp3_subproblem(Lq, i, s_q[4 * M + 2][item], Pq, r2);
+                }
+                s_r2[0][tid] = r2.x; s_r2[1][tid] = r2.y; s_r2[2][tid] = ok ? 1.0f : 0.0f;
             }
             __syncthreads();
-            if (need3) nv = mk(s_res[0][slot], s_res[1][slot]);
+            if (mine && i == 1) {                            // the item's first lane runs linearProgram3's outer scan
+                const Lines Lq = { &s_q[0][item], T };
+                const int qn = __float_as_int(s_q[4 * M + 0][item]), qf = __float_as_int(s_q[4 * M + 1][item]);
+                const float qr = s_q[4 * M + 2][item];
+                V2 res = mk(s_q[4 * M + 3][item], s_q[4 * M + 4][item]);
+                float distance = 0.0f;
+                if (qf == 0 && qn > 0) {                      // i == 0: no projected lines, linearProgram2 returns optVelocity * radius
+                    const V2 d0 = Lq.dir(0), p0 = Lq.point(0);
+                    if (det(d0, p0 - res) > 0.0f) { res = mk(-d0.y * qr, d0.x * qr); distance = det(d0, p0 - res); }
+                }
+                for (int ii = (qf > 1 ? qf : 1); ii < qn; ++ii) {
+                    const V2 di = Lq.dir(ii), pi = Lq.point(ii);
+                    if (det(di, pi - res) > distance) {
+                        const int src = tid + (ii - 1);       // lane of sub-problem ii of this item
+                        if (s_r2[2][src] != 0.0f) res = mk(s_r2[0][src], s_r2[1][src]);
+                        distance = det(di, pi - res);
+                    }
+                }
+                s_res[0][item] = res.x; s_res[1][item] = res.y;
+            }
+            __syncthreads();
         }
+        if (need3) nv = mk(s_res[0][slot], s_res[1][slot]);
     }
 
     if (A.act_only) {                      // crowdsim_orca_act: the robot's ORCA decision only, nothing is mutated

@@ -18,7 +18,6 @@ namespace cs {
 
 unsigned long long g_launches = 0;
 int g_force_generic = 0;   // test hook: route every N through the generic one-thread-per-agent kernel
-int g_force_epw = 0;       // tuning hook: envs per warp of the small-crowd kernel (0 = heuristic)
 
 struct StepArgs {
     KParams k;
@@ -209,25 +208,9 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepA
     }
 }
 
-// Instantiated packings of the small-crowd kernel: largest option <= epw.
-static int flat_snap_epw(int N, int epw)
-{
-    static const int opt[6][3] = {{0, 0, 0}, {1, 4, 16}, {1, 3, 10}, {1, 2, 8}, {1, 2, 6}, {1, 2, 3}};
-    if (N == 5 && epw >= 5) return 5;
-    int best = 1;
-    for (int i = 0; i < 3; ++i) if (opt[N][i] <= epw) best = opt[N][i];
-    return best;
-}
-
-// Packing of the small-crowd kernel: dense (32 / (N + 1) envs per warp). Sparser packings (fewer envs per warp, in-place
-// lp3) give more, less divergent warps, but were measured on B200 at 1 k .. 1 M envs and are never faster: the kernel's
-// instruction stream is almost data-independent, so sparse warps only multiply the instruction count
-// (scripts/tune_epw.py, profiles/r01_tune_epw_n5.txt). crowdsim_debug_force_epw() keeps the knob for re-tuning.
-static int flat_pick_epw(int B, int N)
-{
-    (void)B;
-    return 32 / (N + 1);
-}
+// Packing of the small-crowd kernel is dense (32 / (N + 1) envs per warp). Sparser packings (fewer envs per warp) give
+// more, less divergent warps, but were measured on B200 at 1 k .. 1 M envs and are never faster: the kernel's instruction
+// stream is almost data-independent, so sparse warps only multiply the instruction count (profiles/r01_tune_epw_n5.txt).
 
 static int launch(const crowdsim_params *prm, int B, int N, const crowdsim_state *st, const crowdsim_step_io *io,
                   const crowdsim_episodes *ep, const crowdsim_autoreset *ar, int act_only, cudaStream_t stream)
@@ -258,21 +241,16 @@ static int launch(const crowdsim_params *prm, int B, int N, const crowdsim_state
     A.has_ar = (ar != nullptr && !act_only);
     if (A.has_ar) A.ar = *ar; else memset(&A.ar, 0, sizeof(A.ar));
     if (N >= 1 && N <= 5 && !g_force_generic) {
-        // small crowds: register-resident solver, whole envs per warp (step_flat.cuh). Packing: dense when the batch
-        // fills the chip, sparse (fewer envs per warp, in-place lp3) when it does not -- see flat_pick_epw().
-        const int epw = flat_snap_epw(N, g_force_epw > 0 ? g_force_epw : flat_pick_epw(B, N));
-        const int blocks = (B + 4 * epw - 1) / (4 * epw);
-        #define CS_FLAT(NN, EE, CC) step_flat_kernel<NN, EE, CC><<<blocks, 128, 0, stream>>>(A)
-        switch (N * 100 + epw) {
-            case 101: CS_FLAT(1, 1, false); break;  case 104: CS_FLAT(1, 4, false); break;  case 116: CS_FLAT(1, 16, true); break;
-            case 201: CS_FLAT(2, 1, false); break;  case 203: CS_FLAT(2, 3, false); break;  case 210: CS_FLAT(2, 10, true); break;
-            case 301: CS_FLAT(3, 1, false); break;  case 302: CS_FLAT(3, 2, false); break;  case 308: CS_FLAT(3, 8, true); break;
-            case 401: CS_FLAT(4, 1, false); break;  case 402: CS_FLAT(4, 2, false); break;  case 406: CS_FLAT(4, 6, true); break;
-            case 501: CS_FLAT(5, 1, false); break;  case 502: CS_FLAT(5, 2, false); break;  case 503: CS_FLAT(5, 3, false); break;
-            case 505: CS_FLAT(5, 5, true); break;
-            default: return CROWDSIM_EUNSUPPORTED;
+        // small crowds: register-resident solver, 32 / (N + 1) whole envs per warp (step_flat.cuh)
+        const int epb = 4 * (32 / (N + 1));
+        const int blocks = (B + epb - 1) / epb;
+        switch (N) {
+            case 1: step_flat_kernel<1><<<blocks, 128, 0, stream>>>(A); break;
+            case 2: step_flat_kernel<2><<<blocks, 128, 0, stream>>>(A); break;
+            case 3: step_flat_kernel<3><<<blocks, 128, 0, stream>>>(A); break;
+            case 4: step_flat_kernel<4><<<blocks, 128, 0, stream>>>(A); break;
+            default: step_flat_kernel<5><<<blocks, 128, 0, stream>>>(A); break;
         }
-        #undef CS_FLAT
         ++g_launches;
         return (int)cudaGetLastError();
     }
@@ -304,7 +282,6 @@ extern "C" int crowdsim_orca_act(const crowdsim_params *prm, int B, int N, const
 }
 
 extern "C" void crowdsim_debug_force_generic(int on) { cs::g_force_generic = on; }
-extern "C" void crowdsim_debug_force_epw(int epw) { cs::g_force_epw = epw; }
 
 extern "C" int crowdsim_abi_version(void) { return CROWDSIM_ABI_VERSION; }
 

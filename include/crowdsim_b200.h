@@ -184,8 +184,6 @@ unsigned long long crowdsim_launch_count(void);
 /* Test hook: 1 = use the generic one-thread-per-agent step kernel for every N (default 0: N <= 5 uses the
  * register-resident small-crowd kernel). Both are held to the same bit-exact parity bar. */
 void crowdsim_debug_force_generic(int on);
-/* Tuning hook: envs packed per warp by the small-crowd step kernel (0 = built-in heuristic). */
-void crowdsim_debug_force_epw(int epw);
 
 /* One lockstep env-step for B envs. `ep` and `ar` may be NULL. */
 int crowdsim_step(const crowdsim_params *prm, int B, int N, crowdsim_state *st, crowdsim_step_io *io,
