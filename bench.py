@@ -39,6 +39,7 @@ def parse():
     ap.add_argument('--pools', type=int, default=0, help='independent batches rotated through (0 = enough to exceed L2)')
     ap.add_argument('--rule', default='circle_crossing')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-scale', action='store_true', help='skip the supplementary 1 Mi-env launch measurement')
     return ap.parse_args()
 
 
@@ -320,6 +321,30 @@ def run_ours(args):
                 'algorithmic_bytes_per_launch': B * bytes_per_env, 'avg_launch_us': 1e3 * k_avg,
                 'how': 'CUDA events around %d replays of a graph of %d back-to-back step launches (one per rotating batch)' % (R, pools)}
 
+    # ---- supplementary: the same step kernel when the batch fills the chip (1 Mi envs in ONE launch, state = 665 MB) ----
+    scale = None
+    if rank == 0 and not args.no_scale:
+        Bs = 1 << 20
+        big = BatchedCrowdSim(Bs, device=dev)
+        big.configure(default_config(human_num=N, test_sim=args.rule, train_val_sim=args.rule))
+        big.set_robot_policy('orca')
+        big.reset_seeds(torch.arange(Bs, dtype=torch.int64) % (2 ** 31) + 5000, rule=args.rule)
+        with torch.cuda.stream(main):
+            for _ in range(12):
+                big.step()                                   # into the episodes (agents meet around step 12-20)
+            gb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gb, stream=main):
+            for _ in range(8):
+                big.step()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(main):
+            s0.record(); gb.replay(); s1.record()
+        torch.cuda.synchronize()
+        us = s0.elapsed_time(s1) / 8 * 1e3
+        scale = {'envs_per_launch': Bs, 'us_per_launch': us, 'env_steps_per_s': Bs / us * 1e6, 'achieved_GBps': Bs * bytes_per_env / us / 1e3,
+                 'roofline_frac': Bs * bytes_per_env / us / 1e3 / peak, 'note': 'step kernel only, no resets; shows the issue-bound regime when the chip is full'}
+        del big, gb
+
     # ---- e2e: the public host-facing API (HostStepper.step): pinned HOST buffers in and out every step. The robot is
     # driven from the host like the reference's Explorer loop does it: action up, obs/reward/done/info (+ the robot's
     # next ORCA decision) down, host waits for the results before the next step. ----
@@ -361,7 +386,7 @@ def run_ours(args):
                 'clocks': clocks, 'gpu_launches': int(launches), 'gpu_launches_note': launches_note,
                 'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                         'steps': ke, 'note': 'HostStepper.step(): pinned host buffers <-> device every step (one graph replay + stream sync per step); robot action uploaded, obs/reward/done/info/next ORCA action downloaded'},
-                'episodes': episodes, 'roofline': roofline, 'cpu_baseline': cpu}
+                'episodes': episodes, 'roofline': roofline, 'scale': scale, 'cpu_baseline': cpu}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

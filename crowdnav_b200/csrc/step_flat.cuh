@@ -29,8 +29,13 @@ namespace cs {
 // EPW = 32 / (N + 1) whole envs per warp (dense packing; sparser packings were measured and are never faster, see
 // step_kernel.cu: flat_pick_epw). STAGE is a profiling aid (scripts/latency_probe.cu instantiates cut-down variants to
 // attribute latency); the library only instantiates the full kernel (STAGE = 99).
+// Register budget: asking for 6 resident blocks per SM (<= 80 registers, a few bytes of spill) is neutral at 4096 envs and
+// 9 % faster at 65 k .. 1 M envs than the unconstrained 90-register build (scripts/latency_probe.cu, -DCS_FLAT_MINBLOCKS=1/6/8).
+#ifndef CS_FLAT_MINBLOCKS
+#define CS_FLAT_MINBLOCKS 6
+#endif
 template <int N, int STAGE = 99>
-__global__ void __launch_bounds__(128) step_flat_kernel(const __grid_constant__ StepArgs A)
+__global__ void __launch_bounds__(128, CS_FLAT_MINBLOCKS) step_flat_kernel(const __grid_constant__ StepArgs A)
 {
     if constexpr (STAGE == 0) return;
     using namespace orca;
