@@ -9,7 +9,9 @@ reference does (explorer.py:74-90).
 
 Robot policies:
   'orca'            the robot's ORCA solve is fused into the step kernel (test.py --policy orca)
-  a policy object   anything with .act_batch(env) -> [B][2] float64 device tensor of ActionXY (e.g. policy.BatchedSARL)
+  a policy object   anything with .act_batch(env) -> [B][2] float64 device tensor of ActionXY (policy.make_sarl() ...)
+With update_memory=True the rollout also fills a memory.DeviceReplayMemory like Explorer.update_memory does
+(explorer.py:92-125; imitation-learning returns or target-network bootstraps).
 
 Multi-GPU (torchrun, one process per GPU): the k cases are split into contiguous ranges per rank; there is no data-path
 collective; ONE gather of the per-case result rows (32 B per episode; NCCL on GPU tensors, gloo in the CPU tests) brings
@@ -125,9 +127,9 @@ class BatchedExplorer(object):
 
     def run_k_episodes(self, k, phase, update_memory=False, imitation_learning=False, episode=None,
                        print_failure=False, prefetch_every=2, check_every=32):
-        if update_memory:
-            raise NotImplementedError('replay-memory writes from batched rollouts: SURVEY.md 8(f) row 3')
         env = self.env
+        if update_memory and (self.memory is None or self.gamma is None):
+            raise ValueError('Memory or gamma value is not set!')            # explorer.py:93-94
         first_case = env.case_counter[phase]
         start, n_local = shard_range(k, self.rank, self.world)
         gamma = self.gamma if self.gamma is not None else 0.9
@@ -140,6 +142,10 @@ class BatchedExplorer(object):
         else:
             env.set_robot_policy('external_xy')
         env.reset_seeds(rule=rule, use_queue=True)
+        recorder = None
+        if update_memory:
+            from .memory import TrajectoryRecorder
+            recorder = TrajectoryRecorder(env, self.memory, self.gamma, imitation_learning, self.target_model)
         side = torch.cuda.Stream(device=env.device)
         main = torch.cuda.current_stream(env.device)
         it = 0
@@ -148,10 +154,14 @@ class BatchedExplorer(object):
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
                     env.prefetch()
+            if recorder is not None:
+                recorder.before_step()
             if self.robot_policy == 'orca':
                 env.step()
             else:
                 env.step(self.robot_policy.act_batch(env))
+            if recorder is not None:
+                recorder.after_step()
             it += 1
             if it % check_every == 0 and int(env.state.active.sum()) == 0 and int(env.autoreset.want.sum()) == 0:
                 break

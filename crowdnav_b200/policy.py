@@ -91,6 +91,31 @@ class SARLValueNetwork(nn.Module):
         return self.mlp3(torch.cat([self_state, feat], dim=1))
 
 
+class LSTMRLValueNetwork(nn.Module):
+    """lstm_rl.py:9-65 (ValueNetwork1, or ValueNetwork2 when mlp1_dims is given = "with_interaction_module"): the humans'
+    rows go through an LSTM in the order given, the final hidden state joins the robot's 6 features in an MLP.
+    h0/c0 are created on the input's device (the reference creates them on the CPU, lstm_rl.py:27-28, which breaks
+    under --gpu). With query_env=true the lookahead states reach the network in env order."""
+
+    def __init__(self, input_dim=13, self_state_dim=6, mlp_dims=(150, 100, 100, 1), lstm_hidden_dim=50, mlp1_dims=None):
+        super().__init__()
+        self.self_state_dim = self_state_dim
+        self.lstm_hidden_dim = lstm_hidden_dim
+        if mlp1_dims is not None:
+            self.mlp1 = mlp(input_dim, mlp1_dims)
+        self.mlp = mlp(self_state_dim + lstm_hidden_dim, mlp_dims)
+        self.lstm = nn.LSTM(mlp1_dims[-1] if mlp1_dims is not None else input_dim, lstm_hidden_dim, batch_first=True)
+        self.has_mlp1 = mlp1_dims is not None
+
+    def forward(self, state):
+        b, n, d = state.shape
+        self_state = state[:, 0, :self.self_state_dim]
+        x = self.mlp1(state.reshape(b * n, d)).reshape(b, n, -1) if self.has_mlp1 else state
+        h0 = torch.zeros(1, b, self.lstm_hidden_dim, device=state.device, dtype=state.dtype)
+        _, (hn, _) = self.lstm(x, (h0, torch.zeros_like(h0)))
+        return self.mlp(torch.cat([self_state, hn.squeeze(0)], dim=1))
+
+
 class BatchedValuePolicy(object):
     """Greedy one-step-lookahead policy over a value network (test / val phase of MultiHumanRL.predict and CADRL.predict).
 
@@ -169,4 +194,15 @@ def make_cadrl(gamma=0.9, v_pref=1.0, time_step=0.25, seed=None):
     p = BatchedValuePolicy(CADRLValueNetwork(), gamma, v_pref, time_step, joint=False)
     p.name = 'CADRL'
     p.multiagent_training = False
+    return p
+
+
+def make_lstm_rl(gamma=0.9, v_pref=1.0, time_step=0.25, seed=None, with_interaction_module=False):
+    """LSTM-RL with the reference's default sizes (crowd_nav/configs/policy.config:24-31)."""
+    if seed is not None:
+        torch.manual_seed(seed)
+    net = LSTMRLValueNetwork(mlp_dims=(150, 100, 100, 1), lstm_hidden_dim=50,
+                             mlp1_dims=(150, 100, 100, 50) if with_interaction_module else None)
+    p = BatchedValuePolicy(net, gamma, v_pref, time_step, joint=True)
+    p.name = 'LSTM-RL'
     return p

@@ -6,13 +6,15 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from crowdnav_b200.batched import BatchedCrowdSim, default_config
 
-B, N, pools, K = 4096, 5, 64, 400
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 5
+rule = sys.argv[2] if len(sys.argv) > 2 else 'circle_crossing'
+B, pools, K = 4096, (64 if N <= 5 else 16), 400
 envs = []
 for p in range(pools):
-    env = BatchedCrowdSim(B); env.configure(default_config(human_num=N)); env.set_robot_policy('orca')
+    env = BatchedCrowdSim(B); env.configure(default_config(human_num=N, test_sim=rule, train_val_sim=rule)); env.set_robot_policy('orca')
     env.k_total = 8 * B
     env.track_episodes(env.k_total, gamma=0.9); env.set_case_queue(p * env.k_total, env.k_total, 'train')
-    env.enable_autoreset('circle_crossing'); env.reset_seeds(use_queue=True); env.prefetch(); envs.append(env)
+    env.enable_autoreset(rule); env.reset_seeds(rule=rule, use_queue=True); env.prefetch(); envs.append(env)
 torch.cuda.synchronize()
 for t in range(K):
     env = envs[t % pools]

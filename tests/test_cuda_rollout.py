@@ -71,3 +71,56 @@ def test_sarl_rollout_terminates_and_classifies(cuda_env):
     assert set(np.unique(rows[:, 0]).astype(int)) <= {2, 3, 4}
     assert (rows[:, 1] >= 1).all() and (rows[:, 1] <= 97).all()
     assert (rows[rows[:, 0] == 4, 2] == 25.0).all()
+
+
+def _torch_rotate(rows14):
+    """cadrl.py:187-222 in float32 torch ops (test-side restatement, holonomic)."""
+    s = rows14
+    dx, dy = s[:, 5] - s[:, 0], s[:, 6] - s[:, 1]
+    rot = torch.atan2(dy, dx); c, sn = torch.cos(rot), torch.sin(rot)
+    dg = torch.sqrt(dx * dx + dy * dy)
+    cols = [dg, s[:, 7], torch.zeros_like(dg), s[:, 4], s[:, 2] * c + s[:, 3] * sn, s[:, 3] * c - s[:, 2] * sn,
+            (s[:, 9] - s[:, 0]) * c + (s[:, 10] - s[:, 1]) * sn, (s[:, 10] - s[:, 1]) * c - (s[:, 9] - s[:, 0]) * sn,
+            s[:, 11] * c + s[:, 12] * sn, s[:, 12] * c - s[:, 11] * sn, s[:, 13],
+            torch.sqrt((s[:, 0] - s[:, 9]) ** 2 + (s[:, 1] - s[:, 10]) ** 2), s[:, 4] + s[:, 13]]
+    return torch.stack(cols, dim=1)
+
+
+def test_update_memory_matches_single_env_explorer(cuda_env):
+    """Explorer.update_memory (explorer.py:92-125), imitation learning: the batched rollout (slots = 1, so episodes finish
+    in case order) fills the device memory with the same (state, value) pairs as the single-env Explorer."""
+    import crowdnav_b200.compat as compat
+    from crowdnav_b200.batched import default_config
+    from crowdnav_b200.explorer import BatchedExplorer
+    from crowdnav_b200.memory import DeviceReplayMemory
+    compat.install()
+    import gym
+    from crowd_sim.envs.utils.robot import Robot
+    from crowd_sim.envs.policy.orca import ORCA
+    from crowd_nav.utils.explorer import Explorer
+    k = 10
+
+    class ListMemory(list):
+        def push(self, item):
+            self.append(item)
+
+    class Target(object):                      # MultiHumanRL.transform (multi_human_rl.py:98-107) without occupancy maps
+        def transform(self, state):
+            rows = torch.cat([torch.Tensor([state.self_state + h]) for h in state.human_states], dim=0)
+            return _torch_rotate(rows)
+    cfg = default_config(human_num=5)
+    env1 = gym.make('CrowdSim-v0'); env1.configure(cfg)
+    robot = Robot(cfg, 'robot'); pol = ORCA(); robot.set_policy(pol); env1.set_robot(robot)
+    pol.set_phase('test'); pol.set_env(env1)
+    ref_mem = ListMemory()
+    Explorer(env1, robot, torch.device('cpu'), memory=ref_mem, gamma=0.9, target_policy=Target()).run_k_episodes(
+        k, 'test', update_memory=True, imitation_learning=True)
+
+    env = cuda_env(1, 5)
+    mem = DeviceReplayMemory(4096, 5, env.device)
+    BatchedExplorer(env, 'orca', memory=mem, gamma=0.9).run_k_episodes(k, 'test', update_memory=True, imitation_learning=True,
+                                                                       check_every=1)
+    assert len(mem) == len(ref_mem) > 100
+    ref_states = torch.stack([s for s, _ in ref_mem]); ref_values = torch.cat([v for _, v in ref_mem])
+    assert torch.equal(mem.values[:len(mem), 0].cpu(), ref_values)
+    assert (mem.states[:len(mem)].cpu() - ref_states).abs().max() < 2e-5

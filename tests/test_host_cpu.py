@@ -138,3 +138,95 @@ def test_compat_types_and_module_aliases():
     assert set(policy_factory) == {'linear', 'orca', 'none'} and policy_factory['none']() is None
     assert average([]) == 0 and average([1, 2]) == 1.5
     assert type(gym.make('CrowdSim-v0')).__name__ == 'CrowdSim'
+
+
+def test_bench_reference_arm_emits_contract_json():
+    """bench.py --impl reference (CPU only): one JSON line with the driver's keys, cpu_baseline and a zero-copy e2e block."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '12', '--warmup', '3',
+                          '--envs', '512'], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+                'vs_baseline', 'dtype', 'data', 'config', 'cpu_baseline', 'e2e'):
+        assert key in line, key
+    assert line['impl'] == 'reference' and line['unit'] == 'env-steps/s' and line['value'] > 0 and line['vs_baseline'] is None
+    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
+    assert line['e2e']['h2d_bytes_per_step'] == 0 and line['e2e']['d2h_bytes_per_step'] == 0
+    assert 'workload' in line['config'] and 'model' not in line['config']
+
+
+def test_graft_entry_build_compiles_everything():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+    g.build()
+    from crowdnav_b200 import _abi
+    assert os.path.exists(_abi.LIB_PATH)
+    assert os.path.exists(os.path.join(ROOT, 'oracle', '_build', 'libcrowdsim_oracle.so'))
+    assert os.path.exists(os.path.join(ROOT, 'oracle', '_build', 'librvo2_oracle.so'))
+
+
+def test_device_replay_memory_ring_semantics():
+    """memory.py:4-28: capacity-bounded ring, position wraps, len saturates."""
+    from crowdnav_b200.memory import DeviceReplayMemory
+    m = DeviceReplayMemory(5, 2, 'cpu')
+    m.push_batch(torch.ones(3, 2, 13), torch.tensor([1., 2., 3.]))
+    assert len(m) == 3 and m.position == 3 and not m.is_full()
+    m.push_batch(2 * torch.ones(4, 2, 13), torch.tensor([4., 5., 6., 7.]))
+    assert len(m) == 5 and m.position == 2 and m.is_full()
+    assert m.values[:, 0].tolist() == [6., 7., 3., 4., 5.]
+    s, v = m[0]
+    assert s.shape == (2, 13) and float(v) == 6.0
+    m.clear()
+    assert len(m) == 0
+
+
+def test_il_value_accumulation_equals_reference_formula():
+    """explorer.py:104-105 value_i = sum_t pow(gamma, max(t-i,0)*dt*v_pref) * r_t * [t >= i], accumulated forward in t
+    through the W matrix of TrajectoryRecorder. Same factors, same order; equal to the last ulp or two of float64 (CPython
+    >= 3.12 evaluates sum() with Neumaier compensation, a plain running sum can differ in the last bit) and therefore
+    identical after the float32 cast the reference applies (torch.Tensor([value]))."""
+    gamma, dt, vp, T = 0.9, 0.25, 1.0, 40
+    rng = np.random.RandomState(0)
+    rewards = [float(x) for x in rng.uniform(-0.05, 0.0, T) * (rng.uniform(size=T) < 0.3)]
+    rewards[-1] = 1.0
+    ref = [sum([pow(gamma, max(t - i, 0) * dt * vp) * r * (1 if t >= i else 0) for t, r in enumerate(rewards)]) for i in range(T)]
+    W = torch.tensor([[pow(gamma, (t - i) * dt * vp) if i <= t else 0.0 for i in range(T)] for t in range(T)], dtype=torch.float64)
+    G = torch.zeros(T, dtype=torch.float64)
+    for t, r in enumerate(rewards):
+        G += W[t] * r
+    assert np.abs(G.numpy() - np.array(ref)).max() <= 4e-16
+    assert torch.equal(G.float(), torch.tensor(ref, dtype=torch.float64).float())
+
+
+@pytest.mark.skipif(not os.path.exists('/root/reference/crowd_nav/policy/sarl.py'), reason='reference tree not mounted')
+def test_network_ports_equal_reference_modules():
+    """With the reference's state_dict loaded, the ported networks reproduce the reference modules' outputs exactly
+    (build container only: imports /root/reference through the oracle shims)."""
+    for p in (os.path.join(ROOT, 'oracle', 'shims'), '/root/reference'):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == 'crowd_sim' or k.startswith('crowd_sim.') or k == 'crowd_nav' or k.startswith('crowd_nav.') or k == 'gym' or k.startswith('gym.')}
+    try:
+        from crowd_nav.policy.lstm_rl import ValueNetwork1, ValueNetwork2
+        from crowd_nav.policy.sarl import ValueNetwork as RefSARL
+        from crowd_nav.policy.cadrl import ValueNetwork as RefCADRL
+        from crowdnav_b200.policy import LSTMRLValueNetwork, SARLValueNetwork, CADRLValueNetwork
+        x = torch.randn(9, 5, 13)
+        torch.manual_seed(1)
+        pairs = [(ValueNetwork1(13, 6, [150, 100, 100, 1], 50), LSTMRLValueNetwork()),
+                 (ValueNetwork2(13, 6, [150, 100, 100, 50], [150, 100, 100, 1], 50), LSTMRLValueNetwork(mlp1_dims=(150, 100, 100, 50))),
+                 (RefSARL(13, 6, [150, 100], [100, 50], [150, 100, 100, 1], [100, 100, 1], True, 1.0, 4), SARLValueNetwork())]
+        for ref, mine in pairs:
+            mine.load_state_dict(ref.state_dict())
+            with torch.no_grad():
+                assert torch.equal(ref(x), mine(x))
+        ref, mine = RefCADRL(13, [150, 100, 100, 1]), CADRLValueNetwork()
+        mine.load_state_dict(ref.state_dict())
+        with torch.no_grad():
+            assert torch.equal(ref(x[:, 0]), mine(x[:, 0]))
+    finally:
+        for k in [k for k in sys.modules if k == 'crowd_sim' or k.startswith('crowd_sim.') or k == 'crowd_nav' or k.startswith('crowd_nav.') or k == 'gym' or k.startswith('gym.')]:
+            sys.modules.pop(k)
+        sys.modules.update(saved)
