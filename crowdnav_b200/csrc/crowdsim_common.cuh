@@ -108,6 +108,8 @@ __device__ __forceinline__ void stage_agent(const Stage &s, const KParams &k, in
 // ORCA.predict for agent `a` of local env `le` (a == N: the robot). crowd_sim/envs/policy/orca.py:82-132.
 // Candidate order = reference observation order: other humans in env order, robot last iff visible
 // (crowd_sim.py:324-327); the robot observes all humans (explorer.py:42).
+// linearProgram3 runs in place here: a block-compacted pass with parallel sub-problems (as in step_flat.cuh) was measured
+// for this kernel and is neutral at 4096 envs and 3-12 % slower at 65 k envs (N = 10, 20), so it was not kept.
 __device__ __forceinline__ orca::V2 orca_predict(const Stage &s, const KParams &k, int le, int a, int N, int L,
                                                  double2 pos, double2 goal, double v_pref, int tid, int threads)
 {
@@ -125,23 +127,51 @@ __device__ __forceinline__ orca::V2 orca_predict(const Stage &s, const KParams &
     const float r = rad_view[base + a];
     const float max_speed = (float)v_pref;
 
-    // neighbour list columns live in the (not yet used) proj region
-    float *nd = s.proj + tid; int *ni = reinterpret_cast<int *>(s.proj + (size_t)k.nb_alloc * threads) + tid;
-    int cnt = 0; float range_sq = sqr(k.neighbor_dist);
+    int cnt = 0;
     const int ncand = (is_robot || !k.robot_visible) ? N : L;
-    if (k.max_neighbors > 0)
+    const Lines Lr = { s.lines + tid, threads };
+    const float range_sq0 = sqr(k.neighbor_dist);
+    if (k.max_neighbors > 0 && ncand <= 4 * k.nb_alloc) {
+        // Neighbour selection by repeated arg-min over cached distances: round n picks the nearest not-yet-taken
+        // candidate (ties: lowest scan index, = RVO2's stable insertion order) and builds ORCA line n directly.
+        // Uniform control flow; the data-dependent shifting of insert_neighbor was 19 % of the N = 20 kernel's
+        // instructions at 11.7 / 32 active lanes (profiles/r01_step_generic_n20_ncu_full.txt); measured gain -13 % at N = 20.
+        float *dd = s.proj + tid;                            // distance cache: candidate slot c -> dd[c * threads]
+        for (int j = 0; j < ncand; ++j) {
+            const float2 q = s.pos32[base + j];
+            const float d = abssq(p - mk(q.x, q.y));
+            dd[j * threads] = (j != a && d < range_sq0) ? d : __int_as_float(0x7f800000);   // +inf = not a candidate
+        }
+        unsigned long long taken = 0ull;
+        for (int n = 0; n < k.max_neighbors; ++n) {
+            float best = __int_as_float(0x7f800000); int bj = -1;
+            for (int j = 0; j < ncand; ++j) {
+                const float d = dd[j * threads];
+                if (d < best && !((taken >> j) & 1ull)) { best = d; bj = j; }
+            }
+            if (bj < 0) break;
+            taken |= 1ull << bj;
+            const float2 q = s.pos32[base + bj], w = s.vel32[base + bj];
+            V2 lp, ld;
+            make_line(p, v, r, mk(q.x, q.y), mk(w.x, w.y), rad_view[base + bj], k.inv_time_horizon, k.inv_time_step, lp, ld);
+            Lr.set(cnt++, lp, ld);
+        }
+    } else if (k.max_neighbors > 0) {
+        // RVO2's insertion sort literally (A.2); neighbour list columns live in the (not yet used) proj region
+        float *nd = s.proj + tid; int *ni = reinterpret_cast<int *>(s.proj + (size_t)k.nb_alloc * threads) + tid;
+        float range_sq = range_sq0;
         for (int j = 0; j < ncand; ++j) {
             if (j == a) continue;
             const float2 q = s.pos32[base + j];
             insert_neighbor(abssq(p - mk(q.x, q.y)), j, nd, ni, threads, cnt, k.max_neighbors, range_sq);
         }
-    const Lines Lr = { s.lines + tid, threads };
-    for (int n = 0; n < cnt; ++n) {
-        const int j = ni[n * threads];
-        const float2 q = s.pos32[base + j], w = s.vel32[base + j];
-        V2 lp, ld;
-        make_line(p, v, r, mk(q.x, q.y), mk(w.x, w.y), rad_view[base + j], k.inv_time_horizon, k.inv_time_step, lp, ld);
-        Lr.set(n, lp, ld);
+        for (int n = 0; n < cnt; ++n) {
+            const int j = ni[n * threads];
+            const float2 q = s.pos32[base + j], w = s.vel32[base + j];
+            V2 lp, ld;
+            make_line(p, v, r, mk(q.x, q.y), mk(w.x, w.y), rad_view[base + j], k.inv_time_horizon, k.inv_time_step, lp, ld);
+            Lr.set(n, lp, ld);
+        }
     }
     V2 nv;
     const int fail = lp2(Lr, cnt, max_speed, pref, false, nv);
