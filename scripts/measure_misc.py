@@ -10,7 +10,10 @@ from crowdnav_b200.policy import make_sarl
 out = {}
 
 
-def graph_time(fn, S=20, reps=5):
+def graph_time(fn, S=12, reps=5, env=None):
+    """us per call; with `env` the state is restored before every timed replay so that all replays see the same
+    mid-episode scenes (the step kernel's cost depends on how much the crowd interacts)."""
+    snap = [getattr(env.state, f).clone() for f in env.state.FIELDS] if env is not None else None
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         for _ in range(S):
@@ -18,6 +21,9 @@ def graph_time(fn, S=20, reps=5):
     g.replay(); torch.cuda.synchronize()
     best = 1e9
     for _ in range(reps):
+        if snap is not None:
+            for f, t in zip(env.state.FIELDS, snap):
+                getattr(env.state, f).copy_(t)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1) / S)
@@ -28,8 +34,8 @@ def graph_time(fn, S=20, reps=5):
 for B in (4096, 65536):
     env = BatchedCrowdSim(B); env.configure(default_config(human_num=20, test_sim='square_crossing', train_val_sim='square_crossing'))
     env.set_robot_policy('orca'); env.reset_seeds(torch.arange(B) + 2000, rule='square_crossing')
-    for _ in range(5): env.step()
-    us = graph_time(env.step)
+    for _ in range(8): env.step()
+    us = graph_time(env.step, env=env)
     out['cfg4_step_N20_B%d' % B] = {'us_per_launch': round(us, 2), 'env_steps_per_s': round(B / us * 1e6), 'GBps': round(B * 2074 / us / 1e3, 1)}
     del env
 
