@@ -31,14 +31,47 @@ def discount_table(gamma, time_step, v_pref, n=128):
     return [pow(gamma, t * time_step * v_pref) for t in range(n)]
 
 
+class Slab(object):
+    """One contiguous byte buffer carved into typed tensors (256-byte aligned). The arrays a host-side caller reads after
+    every step (observation, reward, done, info, applied / next action) live in one slab so that ONE device->host copy
+    moves them all (five separate copies cost ~2.5 us of per-copy overhead each on the e2e path)."""
+
+    def __init__(self, layout, device, pin=False):
+        """layout: list of (name, shape, dtype)."""
+        self.layout, self.offsets, off = layout, {}, 0
+        for name, shape, dtype in layout:
+            n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+            self.offsets[name] = (off, n)
+            off += (n + 255) // 256 * 256
+        self.nbytes = off
+        self.buf = torch.zeros(off, dtype=torch.uint8, device=device)
+        if pin:
+            self.buf = self.buf.pin_memory()
+        self.views = {name: self.buf[self.offsets[name][0]:self.offsets[name][0] + self.offsets[name][1]].view(dtype).view(*shape)
+                      for name, shape, dtype in layout}
+
+    def __getitem__(self, name):
+        return self.views[name]
+
+
+def host_visible_layout(B, N):
+    return [('h_pos', (B, N, 2), torch.float64), ('h_vel', (B, N, 2), torch.float64), ('reward', (B,), torch.float64),
+            ('dmin', (B,), torch.float64), ('action_out', (B, 2), torch.float64), ('next_action', (B, 2), torch.float64),
+            ('done', (B,), torch.uint8), ('info', (B,), torch.uint8)]
+
+
 class DeviceState(object):
     """crowdsim_state on device tensors ([B][N][2] / [B][2] / [B] float64)."""
     FIELDS = ('h_pos', 'h_vel', 'h_goal', 'h_attr', 'r_pos', 'r_vel', 'r_goal', 'r_attr', 'r_theta', 'g_time')
 
-    def __init__(self, B, N, device):
+    def __init__(self, B, N, device, slab=None):
         self.B, self.N, self.device = B, N, device
         z = lambda *s: torch.zeros(s, dtype=torch.float64, device=device)  # noqa: E731
-        self.h_pos, self.h_vel, self.h_goal, self.h_attr = z(B, N, 2), z(B, N, 2), z(B, N, 2), z(B, N, 2)
+        if slab is not None:
+            self.h_pos, self.h_vel = slab['h_pos'], slab['h_vel']
+        else:
+            self.h_pos, self.h_vel = z(B, N, 2), z(B, N, 2)
+        self.h_goal, self.h_attr = z(B, N, 2), z(B, N, 2)
         self.r_pos, self.r_vel, self.r_goal, self.r_attr = z(B, 2), z(B, 2), z(B, 2), z(B, 2)
         self.r_theta, self.g_time = z(B), z(B)
         self.active = torch.ones(B, dtype=torch.uint8, device=device)
@@ -162,14 +195,14 @@ class BatchedCrowdSim(object):
         self._alloc()
 
     def _alloc(self):
-        self.state = DeviceState(self.B, self.human_num, self.device)
         B = self.B
+        # everything a host-side caller reads after a step sits in one slab (see Slab)
+        self.out_slab = Slab(host_visible_layout(B, self.human_num), self.device)
+        self.state = DeviceState(B, self.human_num, self.device, slab=self.out_slab)
         self.action = torch.zeros((B, 2), dtype=torch.float64, device=self.device)
-        self.action_out = torch.zeros((B, 2), dtype=torch.float64, device=self.device)
-        self.reward = torch.zeros(B, dtype=torch.float64, device=self.device)
-        self.dmin = torch.zeros(B, dtype=torch.float64, device=self.device)
-        self.done = torch.zeros(B, dtype=torch.uint8, device=self.device)
-        self.info = torch.zeros(B, dtype=torch.uint8, device=self.device)
+        self.action_out, self.next_action = self.out_slab['action_out'], self.out_slab['next_action']
+        self.reward, self.dmin = self.out_slab['reward'], self.out_slab['dmin']
+        self.done, self.info = self.out_slab['done'], self.out_slab['info']
         self._seed32 = torch.zeros(B, dtype=torch.int32, device=self.device)
 
     def set_robot_policy(self, kind):
@@ -314,48 +347,42 @@ class HostStepper(object):
     """env.step() for callers that live on the host (the reference's calling convention: the policy hands a robot
     action to env.step and gets observation, reward, done, info back -- crowd_nav/utils/explorer.py:42-43).
 
-    One call = one CUDA graph replay: H2D copy of the robot actions from pinned memory, the fused step kernel,
-    refill of the consumed next-scene slots (when env.enable_autoreset() was called), the robot's next ORCA decision (optional, so a host
-    loop can drive an ORCA robot), D2H copies of everything a caller reads, then a stream synchronise.
-    Buffers: self.h_action [B][2] (write before step()); results in self.h_pos, h_vel [B][N][2], h_reward, h_done,
-    h_info [B], h_next_action [B][2] (pinned torch tensors; .numpy() views are free)."""
+    One call = one CUDA graph replay: H2D copy of the robot actions from pinned memory, the fused step kernel, a refill of
+    the consumed next-scene slots on a side branch (when env.enable_autoreset() was called), the robot's next ORCA
+    decision (optional, so a host loop can drive an ORCA robot), ONE D2H copy of the slab holding everything a caller
+    reads, then a stream synchronise.
+    Buffers: self.h_action [B][2] (write before step()); results as views of the pinned host slab: self.h_pos, h_vel
+    [B][N][2], h_reward, h_dmin, h_done, h_info [B], h_action_out, h_next_action [B][2] (.numpy() views are free)."""
 
     def __init__(self, env, next_orca_action=True):
         self.env = env
         B, N, dev = env.B, env.human_num, env.device
-        pin = lambda *shape, dtype=torch.float64: torch.zeros(shape, dtype=dtype).pin_memory()  # noqa: E731
-        self.h_action = pin(B, 2)
-        self.h_pos, self.h_vel = pin(B, N, 2), pin(B, N, 2)
-        self.h_reward = pin(B); self.h_done = pin(B, dtype=torch.uint8); self.h_info = pin(B, dtype=torch.uint8)
-        self.h_next_action = pin(B, 2)
-        self.d_action = torch.zeros((B, 2), dtype=torch.float64, device=dev)
-        self.d_next = torch.zeros((B, 2), dtype=torch.float64, device=dev)
+        self.h_action = torch.zeros((B, 2), dtype=torch.float64).pin_memory()
+        self.host_slab = Slab(host_visible_layout(B, N), 'cpu', pin=True)
+        hs = self.host_slab
+        self.h_pos, self.h_vel, self.h_reward, self.h_dmin = hs['h_pos'], hs['h_vel'], hs['reward'], hs['dmin']
+        self.h_done, self.h_info, self.h_action_out, self.h_next_action = hs['done'], hs['info'], hs['action_out'], hs['next_action']
         self.stream = torch.cuda.Stream(device=dev)
+        self.side = torch.cuda.Stream(device=dev)
         self.h2d_bytes = self.h_action.numel() * 8
-        self.d2h_bytes = sum(t.numel() * t.element_size() for t in (self.h_pos, self.h_vel, self.h_reward, self.h_done, self.h_info))
-        if next_orca_action:
-            self.d2h_bytes += self.h_next_action.numel() * 8
+        self.d2h_bytes = hs.nbytes
         self.kernels_per_step = 1 + (1 if env.autoreset is not None else 0) + (1 if next_orca_action else 0)
 
         def body():
-            self.d_action.copy_(self.h_action, non_blocking=True)
-            env.step(self.d_action)                    # installs prefetched scenes of finished envs when auto-reset is on
+            env.action.copy_(self.h_action, non_blocking=True)
+            env.step(env.action)                       # installs prefetched scenes of finished envs when auto-reset is on
             if env.autoreset is not None:              # refill consumed slots on a side branch of the graph
                 self.side.wait_stream(self.stream)
                 with torch.cuda.stream(self.side):
                     env.prefetch()
             if next_orca_action:
-                env.orca_act(self.d_next)
-                self.h_next_action.copy_(self.d_next, non_blocking=True)
-            self.h_pos.copy_(env.state.h_pos, non_blocking=True); self.h_vel.copy_(env.state.h_vel, non_blocking=True)
-            self.h_reward.copy_(env.reward, non_blocking=True); self.h_done.copy_(env.done, non_blocking=True)
-            self.h_info.copy_(env.info, non_blocking=True)
+                env.orca_act(env.next_action)
+            hs.buf.copy_(env.out_slab.buf, non_blocking=True)
             if env.autoreset is not None:
                 self.stream.wait_stream(self.side)     # join: the refill must be complete before the next step
-        self.side = torch.cuda.Stream(device=dev)
         with torch.cuda.stream(self.stream):
             body()                                     # warm-up outside capture (lazy inits)
-        self.stream.synchronize()
+        self.stream.synchronize(); self.side.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, stream=self.stream):
             body()
