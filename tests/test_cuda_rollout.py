@@ -124,3 +124,28 @@ def test_update_memory_matches_single_env_explorer(cuda_env):
     ref_states = torch.stack([s for s, _ in ref_mem]); ref_values = torch.cat([v for _, v in ref_mem])
     assert torch.equal(mem.values[:len(mem), 0].cpu(), ref_values)
     assert (mem.states[:len(mem)].cpu() - ref_states).abs().max() < 2e-5
+
+
+def test_host_stepper_matches_oracle(cuda_env, oracle):
+    """The host-facing step API (pinned buffers in/out, one CUDA graph per call): driving the robot from the host with the
+    'next action' the device computed reproduces the oracle's ORCA-robot episodes bit-exactly, array for array."""
+    from crowdnav_b200.batched import HostStepper
+    from crowdnav_b200 import _abi
+    B, N = 300, 5
+    host = oracle.HostState(B, N); io = oracle.HostStepIO(B)
+    oracle.reset(host, np.arange(B) + 1000)
+    env = cuda_env(B, N, robot_policy='external_xy')
+    env.state.load_host(host)
+    stepper = HostStepper(env, next_orca_action=True)          # its warm-up + capture passes step the env: reload the scene
+    env.state.load_host(host)
+    prm_ext = oracle.default_params(robot_policy=_abi.ROBOT_EXTERNAL_XY)
+    act = oracle.orca_act(oracle.default_params(), host)
+    for t in range(25):
+        stepper.h_action.copy_(torch.from_numpy(act))
+        (h_pos, h_vel), rew, done, info = stepper.step()
+        io.action[...] = act
+        oracle.step(prm_ext, host, io)
+        assert np.array_equal(h_pos.numpy(), host.h_pos) and np.array_equal(h_vel.numpy(), host.h_vel), t
+        assert np.array_equal(rew.numpy(), io.reward) and np.array_equal(done.numpy(), io.done) and np.array_equal(info.numpy(), io.info)
+        act = oracle.orca_act(oracle.default_params(), host)
+        assert np.array_equal(stepper.h_next_action.numpy(), act), t
