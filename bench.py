@@ -39,6 +39,7 @@ def parse():
     ap.add_argument('--pools', type=int, default=0, help='independent batches rotated through (0 = enough to exceed L2)')
     ap.add_argument('--rule', default='circle_crossing')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-python-loop', action='store_true', help='reference arm: skip the reference-shaped Python loop timing')
     ap.add_argument('--no-scale', action='store_true', help='skip the supplementary 1 Mi-env launch measurement')
     return ap.parse_args()
 
@@ -163,6 +164,17 @@ def run_reference(args):
         one()
     dt = time.perf_counter() - t0
     v = B * args.steps / dt
+    # context: the same path with the reference's STRUCTURE (interpreter-bound Python loop around a native rvo2 step,
+    # oracle/pyloop.py) on a bounded sample -- the reference's real files cannot travel to this box
+    py = None
+    if not args.no_python_loop:
+        import pyloop
+        one, n1 = pyloop.timed_rate(list(range(1000, 1064)), N, args.rule)
+        allc, n2, procs = pyloop.timed_rate_all_cores(list(range(1000, 1000 + 16 * min(os.cpu_count() or 1, 64))), N, args.rule,
+                                                      procs=min(os.cpu_count() or 1, 64))
+        py = {'one_core_env_steps_per_s': one, 'all_cores_env_steps_per_s': allc, 'processes': procs,
+              'sample': '%d + %d env-steps of the seeded test cases; Python loop + C rvo2 shim (oracle/pyloop.py); the reference\'s '
+                        'own Python measured 4.8 k env-steps/s/core in the build container (DESIGN.md 6)' % (n1, n2)}
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'env-steps/s', 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f64 state + f32 ORCA solver', 'data': 'synthetic',
@@ -171,7 +183,7 @@ def run_reference(args):
                              'sample': '%d lockstep passes over a %d-env batch per run; C restatement of the reference loop '
                                        '(oracle/crowdsim_oracle.c, OpenMP over envs, thread count calibrated, host has %d logical CPUs)' % (args.steps, B, os.cpu_count() or 0)},
             'e2e': {'value': v, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-            'gpu_launches': 0}
+            'python_loop': py, 'gpu_launches': 0}
     print(json.dumps(line))
 
 

@@ -207,3 +207,18 @@ def test_autoreset_case_queue_reproduces_suite(oracle, slots):
         assert ep.res_return[i] == float(c['return'])
         r, _ = scene_arrays(c['final'])
         assert (ep.res_final_rpos[i] == r[:2]).all()
+
+
+@pytest.mark.parametrize('name', ['circle5_invisible', 'square5_invisible', 'circle5_visible'])
+def test_python_loop_restatement_reproduces_reference(name):
+    """oracle/pyloop.py (the reference's loop structure restated in Python on the rvo2 shim) against the golden suites:
+    a third independent restatement, also used as the reference-shaped CPU timing in bench.py --impl reference."""
+    import pyloop
+    N, rule, vis, _ = SUITES[name]
+    cases = load_golden('suite_' + name)['cases'][:40]
+    for c in cases:
+        info, steps, t, rxy = pyloop.run_episode(1000 + c['case'], N, rule, bool(vis))
+        assert (info, steps) == (c['info'], c['steps']), c['case']
+        assert t == float(c['global_time'])
+        r, _ = scene_arrays(c['final'])
+        assert rxy == (r[0], r[1])
