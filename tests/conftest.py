@@ -27,7 +27,8 @@ def cuda_env():
     """Factory for BatchedCrowdSim on cuda:0; fails loudly if the CUDA library is missing."""
     import torch
     assert torch.cuda.is_available(), 'gpu-marked test without a GPU'
-    from crowdnav_b200 import _abi
+    from crowdnav_b200 import _abi, build as cuda_build
+    cuda_build.build()              # (re)build in-tree with nvcc if the library is missing or stale; never a CPU fallback
     _abi.load()
     from crowdnav_b200.batched import BatchedCrowdSim, default_config
 
