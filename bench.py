@@ -31,8 +31,8 @@ ALG_BYTES = lambda n: 8 * (19 + 12 * n) + 2      # 634 B at N=5,
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=6400)
-    ap.add_argument('--warmup', type=int, default=640)
+    ap.add_argument('--steps', type=int, default=25600)
+    ap.add_argument('--warmup', type=int, default=2560)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--envs', type=int, default=4096, help='envs per batch per GPU')
     ap.add_argument('--humans', type=int, default=5)
@@ -52,38 +52,57 @@ def load_peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+class ClockSampler(object):
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe): one long-lived
+    `nvidia-smi -lms 20` child whose lines are timestamped on arrival; only samples that fall between mark_start() and
+    mark_stop() are used (the child is started earlier so that its start-up cost is outside the window)."""
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
     def __init__(self, index=0):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.rows, self.t0, self.t1 = [], None, None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                          '-lms', '20'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
 
-    def run(self):
-        while not self._stop_evt.is_set():
-            try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits'],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.splitlines()[0].split(',')])
-            except Exception:
-                pass
-            self._stop_evt.wait(0.1)
+    def _read(self):
+        if self.proc is None:
+            return
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(',')]))
+
+    def mark_start(self):
+        self.t0 = time.perf_counter()
+
+    def mark_stop(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
-        self._stop_evt.set()
-        self.join(timeout=6)
-        sm = sorted(int(float(r[1])) for r in self.rows if r[1].replace('.', '').isdigit())
-        mx = [int(float(r[2])) for r in self.rows if r[2].replace('.', '').isdigit()]
+        if self.proc is not None:
+            self.proc.terminate()            # the child we started, by handle
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        self.thread.join(timeout=5)
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or 1e30) and len(r) >= 7]
+        used = inside if inside else [r for _, r in self.rows[-3:] if len(r) >= 7]
+        num = lambda v: int(float(v)) if v.replace('.', '', 1).isdigit() else None  # noqa: E731
+        sm = sorted(x for x in (num(r[0]) for r in used) if x is not None)
+        mx = [x for x in (num(r[1]) for r in used) if x is not None]
+        pw = [float(r[2]) for r in used if r[2].replace('.', '', 1).isdigit()]
         reasons = set()
-        for r in self.rows:
-            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[4:8]):
+        for r in used:
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
                 if v.lower().startswith('active'):
                     reasons.add(name)
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(self.rows)}
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': sorted(reasons),
+                'samples': len(inside), 'power_w_max': max(pw) if pw else None,
+                'note': None if inside else 'timed region shorter than the sampling period: nearest samples used'}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -269,16 +288,18 @@ def run_ours(args):
     torch.cuda.synchronize()
     g_warm = capture(max(W, 3))
     g_timed = capture(K)
+    sampler = ClockSampler(local)
     with torch.cuda.stream(main):
         g_warm.replay()
     barrier()
-    sampler = ClockSampler(local); sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark_start()
     with torch.cuda.stream(main):
         e0.record()
         g_timed.replay()
         e1.record()
     barrier()
+    sampler.mark_stop()
     launches = 2 * K
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
