@@ -17,38 +17,43 @@
 // is at base[(k * 4 + c) * stride + t] -- consecutive threads hit consecutive banks, no conflicts.
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
+
+// The solver is plain arithmetic: it also compiles for the host, which lets a CPU test fuzz it against the C oracle
+// with millions of random line sets (tests/native/lp_fuzz.cu) without spending GPU time.
+#define ORCA_HD __host__ __device__
 
 namespace orca {
 
 constexpr float kEps = 0.00001f;   // RVO_EPSILON
 
 struct V2 { float x, y; };
-__device__ __forceinline__ V2 mk(float x, float y) { V2 r; r.x = x; r.y = y; return r; }
-__device__ __forceinline__ V2 operator+(V2 a, V2 b) { return mk(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ V2 operator-(V2 a, V2 b) { return mk(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ V2 operator-(V2 a) { return mk(-a.x, -a.y); }
-__device__ __forceinline__ V2 operator*(float s, V2 a) { return mk(s * a.x, s * a.y); }
-__device__ __forceinline__ V2 vdiv(V2 a, float s) { const float inv = 1.0f / s; return mk(a.x * inv, a.y * inv); }
-__device__ __forceinline__ float dot(V2 a, V2 b) { return a.x * b.x + a.y * b.y; }
-__device__ __forceinline__ float det(V2 a, V2 b) { return a.x * b.y - a.y * b.x; }
-__device__ __forceinline__ float abssq(V2 a) { return dot(a, a); }
-__device__ __forceinline__ float sqr(float a) { return a * a; }
-__device__ __forceinline__ V2 normalize(V2 a) { return vdiv(a, sqrtf(abssq(a))); }
+ORCA_HD __forceinline__ V2 mk(float x, float y) { V2 r; r.x = x; r.y = y; return r; }
+ORCA_HD __forceinline__ V2 operator+(V2 a, V2 b) { return mk(a.x + b.x, a.y + b.y); }
+ORCA_HD __forceinline__ V2 operator-(V2 a, V2 b) { return mk(a.x - b.x, a.y - b.y); }
+ORCA_HD __forceinline__ V2 operator-(V2 a) { return mk(-a.x, -a.y); }
+ORCA_HD __forceinline__ V2 operator*(float s, V2 a) { return mk(s * a.x, s * a.y); }
+ORCA_HD __forceinline__ V2 vdiv(V2 a, float s) { const float inv = 1.0f / s; return mk(a.x * inv, a.y * inv); }
+ORCA_HD __forceinline__ float dot(V2 a, V2 b) { return a.x * b.x + a.y * b.y; }
+ORCA_HD __forceinline__ float det(V2 a, V2 b) { return a.x * b.y - a.y * b.x; }
+ORCA_HD __forceinline__ float abssq(V2 a) { return dot(a, a); }
+ORCA_HD __forceinline__ float sqr(float a) { return a * a; }
+ORCA_HD __forceinline__ V2 normalize(V2 a) { return vdiv(a, sqrtf(abssq(a))); }
 
 // Per-thread column view of a line array in shared memory.
 struct Lines {
     float *base;   // already offset by the thread's column
     int stride;    // threads per block (column count)
-    __device__ __forceinline__ V2 point(int k) const { return mk(base[(k * 4 + 0) * stride], base[(k * 4 + 1) * stride]); }
-    __device__ __forceinline__ V2 dir(int k) const { return mk(base[(k * 4 + 2) * stride], base[(k * 4 + 3) * stride]); }
-    __device__ __forceinline__ void set(int k, V2 p, V2 d) const {
+    ORCA_HD __forceinline__ V2 point(int k) const { return mk(base[(k * 4 + 0) * stride], base[(k * 4 + 1) * stride]); }
+    ORCA_HD __forceinline__ V2 dir(int k) const { return mk(base[(k * 4 + 2) * stride], base[(k * 4 + 3) * stride]); }
+    ORCA_HD __forceinline__ void set(int k, V2 p, V2 d) const {
         base[(k * 4 + 0) * stride] = p.x; base[(k * 4 + 1) * stride] = p.y;
         base[(k * 4 + 2) * stride] = d.x; base[(k * 4 + 3) * stride] = d.y;
     }
 };
 
 // A.2 insertAgentNeighbor on per-thread shared-memory columns nd[k*stride], ni[k*stride].
-__device__ __forceinline__ void insert_neighbor(float dist_sq, int other, float *nd, int *ni, int stride,
+ORCA_HD __forceinline__ void insert_neighbor(float dist_sq, int other, float *nd, int *ni, int stride,
                                                 int &cnt, int max_nb, float &range_sq)
 {
     if (dist_sq < range_sq) {
@@ -61,7 +66,7 @@ __device__ __forceinline__ void insert_neighbor(float dist_sq, int other, float 
 }
 
 // A.3 one ORCA half-plane.
-__device__ __forceinline__ void make_line(V2 p, V2 v, float r, V2 po, V2 vo, float ro, float inv_th, float inv_dt,
+ORCA_HD __forceinline__ void make_line(V2 p, V2 v, float r, V2 po, V2 vo, float ro, float inv_th, float inv_dt,
                                           V2 &point, V2 &dir)
 {
     const V2 rel_pos = po - p;
@@ -99,7 +104,7 @@ __device__ __forceinline__ void make_line(V2 p, V2 v, float r, V2 po, V2 vo, flo
 }
 
 // A.4 lp1
-__device__ __forceinline__ bool lp1(const Lines &L, int line_no, float radius, V2 opt, bool dir_opt, V2 &result)
+ORCA_HD __forceinline__ bool lp1(const Lines &L, int line_no, float radius, V2 opt, bool dir_opt, V2 &result)
 {
     const V2 lp = L.point(line_no), ld = L.dir(line_no);
     const float dp = dot(lp, ld);
@@ -134,7 +139,7 @@ __device__ __forceinline__ bool lp1(const Lines &L, int line_no, float radius, V
 }
 
 // A.4 lp2
-__device__ __forceinline__ int lp2(const Lines &L, int n, float radius, V2 opt, bool dir_opt, V2 &result)
+ORCA_HD __forceinline__ int lp2(const Lines &L, int n, float radius, V2 opt, bool dir_opt, V2 &result)
 {
     if (dir_opt)                          result = mk(opt.x * radius, opt.y * radius);
     else if (abssq(opt) > sqr(radius)) { const V2 nv = normalize(opt); result = mk(nv.x * radius, nv.y * radius); }
@@ -150,7 +155,7 @@ __device__ __forceinline__ int lp2(const Lines &L, int n, float radius, V2 opt, 
 
 // Projected lines of line i onto lines j < i (the loop body of linearProgram3): written to P in j order, parallel
 // same-direction lines skipped. Returns their number.
-__device__ __forceinline__ int lp3_project(const Lines &L, int i, const Lines &P)
+ORCA_HD __forceinline__ int lp3_project(const Lines &L, int i, const Lines &P)
 {
     const V2 li_p = L.point(i), li_d = L.dir(i);
     int np = 0;
@@ -173,15 +178,35 @@ __device__ __forceinline__ int lp3_project(const Lines &L, int i, const Lines &P
 // The sub-problem of line i inside linearProgram3: linearProgram2 over the projected lines, direction optimisation,
 // STARTING FROM optVelocity * radius -- it does not depend on the running result, only on the lines. Returns false if
 // it fails (RVO2 then keeps the current result).
-__device__ __forceinline__ bool lp3_subproblem(const Lines &L, int i, float radius, const Lines &P, V2 &r2)
+ORCA_HD __forceinline__ bool lp3_subproblem(const Lines &L, int i, float radius, const Lines &P, V2 &r2)
 {
     const V2 li_d = L.dir(i);
     const int np = lp3_project(L, i, P);
     return !(lp2(P, np, radius, mk(-li_d.y, li_d.x), true, r2) < np);
 }
 
+// linearProgram3's outer loop given the (independent) sub-problem results: `sub(ii, r2)` returns whether sub-problem ii
+// succeeded and its point. Line 0 has no projected lines: linearProgram2 over the empty set returns optVelocity * radius.
+template <typename SubFn>
+ORCA_HD __forceinline__ void lp3_outer_scan(const Lines &L, int n, int begin, float radius, V2 &result, SubFn sub)
+{
+    float distance = 0.0f;
+    if (begin == 0 && n > 0) {
+        const V2 d0 = L.dir(0), p0 = L.point(0);
+        if (det(d0, p0 - result) > 0.0f) { result = mk(-d0.y * radius, d0.x * radius); distance = det(d0, p0 - result); }
+    }
+    for (int ii = (begin > 1 ? begin : 1); ii < n; ++ii) {
+        const V2 di = L.dir(ii), pi = L.point(ii);
+        if (det(di, pi - result) > distance) {
+            V2 r2;
+            if (sub(ii, r2)) result = r2;              // on failure the current result is kept
+            distance = det(di, pi - result);
+        }
+    }
+}
+
 // A.4 lp3 (numObstLines == 0: crowd_sim never adds obstacles)
-static __device__ __noinline__ void lp3(const Lines &L, int n, int begin, float radius, const Lines &P, V2 &result)
+static ORCA_HD __noinline__ void lp3(const Lines &L, int n, int begin, float radius, const Lines &P, V2 &result)
 {
     float distance = 0.0f;
     for (int i = begin; i < n; ++i) {

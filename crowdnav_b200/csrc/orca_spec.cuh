@@ -31,7 +31,7 @@ template <int M> struct RegLines { V2 p[M], d[M]; };
 // loads + neighbour scan + 5 lines per solve; a fully branch-free form (overlap folded in, no per-line valid branch)
 // 7.0 us -- the extra arithmetic costs more than the removed divergence, the chains do not overlap in practice.
 // Keeping it out of line (__noinline__, to shrink the 5 k-instruction kernel) was also measured: 9.6 vs 9.2 us per launch.
-__device__ __forceinline__ void make_line_sel(V2 p, V2 v, float r, V2 po, V2 vo, float ro, float inv_th, float inv_dt,
+ORCA_HD __forceinline__ void make_line_sel(V2 p, V2 v, float r, V2 po, V2 vo, float ro, float inv_th, float inv_dt,
                                               V2 &point, V2 &dir)
 {
     const V2 rel_pos = po - p;
@@ -74,7 +74,7 @@ __device__ __forceinline__ void make_line_sel(V2 p, V2 v, float r, V2 po, V2 vo,
 // lp1 candidates of every position (speculative). valid[i]: position i holds a line (absent positions never constrain).
 // CNT = number of leading positions to evaluate (compile time, <= M).
 template <int M, int CNT>
-__device__ __forceinline__ void lp1_all(const RegLines<M> &R, const bool (&valid)[M], float radius, V2 opt, bool dir_opt,
+ORCA_HD __forceinline__ void lp1_all(const RegLines<M> &R, const bool (&valid)[M], float radius, V2 opt, bool dir_opt,
                                         V2 (&cand)[M], bool (&feas)[M])
 {
     #pragma unroll
@@ -110,7 +110,7 @@ __device__ __forceinline__ void lp1_all(const RegLines<M> &R, const bool (&valid
 
 // linearProgram2 as a scan over precomputed candidates. Returns the failing position or count.
 template <int M, int CNT>
-__device__ __forceinline__ int lp2_scan(const RegLines<M> &R, const bool (&valid)[M], int count, const V2 (&cand)[M], const bool (&feas)[M],
+ORCA_HD __forceinline__ int lp2_scan(const RegLines<M> &R, const bool (&valid)[M], int count, const V2 (&cand)[M], const bool (&feas)[M],
                                         V2 init, V2 &result)
 {
     result = init;
@@ -124,7 +124,7 @@ __device__ __forceinline__ int lp2_scan(const RegLines<M> &R, const bool (&valid
 }
 
 // Initial point of linearProgram2 (closest-point mode).
-__device__ __forceinline__ V2 lp2_init(V2 opt, float radius)
+ORCA_HD __forceinline__ V2 lp2_init(V2 opt, float radius)
 {
     if (abssq(opt) > sqr(radius)) { const V2 nv = normalize(opt); return mk(nv.x * radius, nv.y * radius); }
     return opt;

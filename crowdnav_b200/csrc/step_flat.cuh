@@ -195,19 +195,11 @@ __global__ void __launch_bounds__(128, CS_FLAT_MINBLOCKS) step_flat_kernel(const
                 const int qn = __float_as_int(s_q[4 * M + 0][item]), qf = __float_as_int(s_q[4 * M + 1][item]);
                 const float qr = s_q[4 * M + 2][item];
                 V2 res = mk(s_q[4 * M + 3][item], s_q[4 * M + 4][item]);
-                float distance = 0.0f;
-                if (qf == 0 && qn > 0) {                      // i == 0: no projected lines, linearProgram2 returns optVelocity * radius
-                    const V2 d0 = Lq.dir(0), p0 = Lq.point(0);
-                    if (det(d0, p0 - res) > 0.0f) { res = mk(-d0.y * qr, d0.x * qr); distance = det(d0, p0 - res); }
-                }
-                for (int ii = (qf > 1 ? qf : 1); ii < qn; ++ii) {
-                    const V2 di = Lq.dir(ii), pi = Lq.point(ii);
-                    if (det(di, pi - res) > distance) {
-                        const int src = tid + (ii - 1);       // lane of sub-problem ii of this item
-                        if (s_r2[2][src] != 0.0f) res = mk(s_r2[0][src], s_r2[1][src]);
-                        distance = det(di, pi - res);
-                    }
-                }
+                lp3_outer_scan(Lq, qn, qf, qr, res, [&](int ii, V2 &r2) {
+                    const int src = tid + (ii - 1);               // lane of sub-problem ii of this item
+                    r2 = mk(s_r2[0][src], s_r2[1][src]);
+                    return s_r2[2][src] != 0.0f;
+                });
                 s_res[0][item] = res.x; s_res[1][item] = res.y;
             }
             __syncthreads();

@@ -1,0 +1,105 @@
+// lp_fuzz.cu -- CPU fuzz test (test infrastructure): the CUDA solver's arithmetic compiled FOR THE HOST
+// (crowdnav_b200/csrc/orca_device.cuh, orca_spec.cuh are __host__ __device__) against the C oracle
+// (oracle/rvo2_f32.h) on millions of random ORCA problems, bit for bit:
+//   A  make_line / make_line_sel            vs  orc_make_line
+//   B  sequential lp2 + lp3 (shared-memory-column code path of the generic kernel, n <= 10)   vs  orc_lp2 / orc_lp3
+//   C  speculative lp1_all + lp2_scan (register path of the small-crowd kernel, n <= 5)        vs  orc_lp2
+//   D  lp3 as independent per-line sub-problems + lp3_outer_scan (the lane-parallel pass)      vs  orc_lp3
+// Build (tests/test_native_cpu.py): nvcc -O2 --fmad=false -Xcompiler -ffp-contract=off -std=c++17 lp_fuzz.cu
+// Usage: lp_fuzz <cases> <seed>; prints coverage counters; exit code 0 iff every comparison was bit-identical.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdint>
+#include "../../crowdnav_b200/csrc/orca_device.cuh"
+#include "../../crowdnav_b200/csrc/orca_spec.cuh"
+extern "C" {
+#include "../../oracle/rvo2_f32.h"
+}
+
+static uint64_t rng_state;
+static inline uint32_t rnd() { rng_state ^= rng_state << 13; rng_state ^= rng_state >> 7; rng_state ^= rng_state << 17; return (uint32_t)(rng_state >> 16); }
+static inline float uni(float a, float b) { return a + (b - a) * (rnd() / 4294967296.0f); }
+static inline bool same(float a, float b) { return memcmp(&a, &b, 4) == 0; }
+
+template <int M>
+static bool check_case(int n, const orc_line *ol, float radius, orc_v2 opt, long *cov)
+{
+    using namespace orca;
+    // ---- oracle ----
+    orc_v2 ores; const int ofail = orc_lp2(ol, n, radius, opt, 0, &ores);
+    orc_v2 ores3 = ores; if (ofail < n) orc_lp3(ol, n, ofail, radius, &ores3);
+    cov[0] += (ofail < n);
+    // ---- B: sequential code on column-layout arrays (stride 1) ----
+    float lbuf[4 * 16], pbuf[4 * 16];
+    const Lines L = { lbuf, 1 }, P = { pbuf, 1 };
+    for (int k = 0; k < n; ++k) L.set(k, mk(ol[k].point.x, ol[k].point.y), mk(ol[k].dir.x, ol[k].dir.y));
+    V2 r; const int f = lp2(L, n, radius, mk(opt.x, opt.y), false, r);
+    if (f != ofail || !same(r.x, ores.x) || !same(r.y, ores.y)) { printf("B lp2 mismatch n=%d\n", n); return false; }
+    V2 r3 = r; if (f < n) lp3(L, n, f, radius, P, r3);
+    if (!same(r3.x, ores3.x) || !same(r3.y, ores3.y)) { printf("B lp3 mismatch n=%d fail=%d\n", n, f); return false; }
+    // ---- D: lp3 as independent sub-problems + outer scan ----
+    if (f < n) {
+        V2 sub_r[16]; bool sub_ok[16];
+        for (int i = 1; i < n; ++i) sub_ok[i] = lp3_subproblem(L, i, radius, P, sub_r[i]);
+        V2 rd = r;
+        lp3_outer_scan(L, n, f, radius, rd, [&](int ii, V2 &r2) { r2 = sub_r[ii]; return sub_ok[ii]; });
+        if (!same(rd.x, ores3.x) || !same(rd.y, ores3.y)) { printf("D lp3 sub-problem mismatch n=%d fail=%d\n", n, f); return false; }
+    }
+    // ---- C: speculative register path (n <= M) ----
+    if (n <= M) {
+        RegLines<M> R; bool valid[M];
+        for (int k = 0; k < M; ++k) { valid[k] = k < n; R.p[k] = k < n ? mk(ol[k].point.x, ol[k].point.y) : mk(0, 0); R.d[k] = k < n ? mk(ol[k].dir.x, ol[k].dir.y) : mk(0, 0); }
+        V2 cand[M]; bool feas[M];
+        lp1_all<M, M>(R, valid, radius, mk(opt.x, opt.y), false, cand, feas);
+        V2 rs; const int fs = lp2_scan<M, M>(R, valid, n, cand, feas, lp2_init(mk(opt.x, opt.y), radius), rs);
+        if (fs != ofail || !same(rs.x, ores.x) || !same(rs.y, ores.y)) { printf("C speculative lp2 mismatch n=%d (fail %d vs %d)\n", n, fs, ofail); return false; }
+        cov[1]++;
+    }
+    return true;
+}
+
+int main(int argc, char **argv)
+{
+    const long cases = argc > 1 ? atol(argv[1]) : 200000;
+    rng_state = argc > 2 ? strtoull(argv[2], nullptr, 10) * 2654435761ull + 88172645463325252ull : 88172645463325252ull;
+    long cov[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    using namespace orca;
+    for (long c = 0; c < cases; ++c) {
+        const int kind = rnd() % 4;
+        const int n = 1 + rnd() % ((kind == 3) ? 10 : 5);
+        orc_line ol[16];
+        const float radius = uni(0.5f, 1.5f);
+        orc_v2 opt = orc_mk(uni(-1.2f, 1.2f), uni(-1.2f, 1.2f));
+        if (kind <= 1 || kind == 3) {
+            // lines from a random crowd around an agent at the origin (kind 1: tight -> overlaps, infeasible LPs)
+            const float spread = (kind == 1) ? 1.0f : 4.0f;
+            const orc_v2 p = orc_mk(0.f, 0.f), v = orc_mk(uni(-1, 1), uni(-1, 1));
+            for (int k = 0; k < n; ++k) {
+                const orc_v2 po = orc_mk(uni(-spread, spread), uni(-spread, spread)), vo = orc_mk(uni(-1, 1), uni(-1, 1));
+                const float r = uni(0.2f, 0.5f), ro = uni(0.2f, 0.5f);
+                ol[k] = orc_make_line(p, v, r, po, vo, ro, 1.0f / 5.0f, 0.25f);
+                // ---- A: line construction ----
+                V2 lp, ld, sp, sd;
+                make_line(mk(p.x, p.y), mk(v.x, v.y), r, mk(po.x, po.y), mk(vo.x, vo.y), ro, 1.0f / 5.0f, 1.0f / 0.25f, lp, ld);
+                make_line_sel(mk(p.x, p.y), mk(v.x, v.y), r, mk(po.x, po.y), mk(vo.x, vo.y), ro, 1.0f / 5.0f, 1.0f / 0.25f, sp, sd);
+                if (!same(lp.x, ol[k].point.x) || !same(lp.y, ol[k].point.y) || !same(ld.x, ol[k].dir.x) || !same(ld.y, ol[k].dir.y) ||
+                    !same(sp.x, lp.x) || !same(sp.y, lp.y) || !same(sd.x, ld.x) || !same(sd.y, ld.y)) { printf("A line mismatch\n"); return 1; }
+                const float dsq = po.x * po.x + po.y * po.y; cov[2] += (dsq <= (r + ro) * (r + ro));
+            }
+        } else {
+            // adversarial: arbitrary half-planes incl. exactly parallel / anti-parallel / duplicated lines and far-away points
+            for (int k = 0; k < n; ++k) {
+                const float ang = uni(-3.2f, 3.2f);
+                ol[k].dir = orc_mk(cosf(ang), sinf(ang));
+                ol[k].point = orc_mk(uni(-2, 2), uni(-2, 2));
+                if (k > 0 && rnd() % 4 == 0) { ol[k].dir = ol[rnd() % k].dir; cov[3]++; }
+                if (k > 0 && rnd() % 6 == 0) { const orc_v2 d = ol[rnd() % k].dir; ol[k].dir = orc_mk(-d.x, -d.y); cov[3]++; }
+                if (k > 0 && rnd() % 12 == 0) ol[k] = ol[rnd() % k];
+            }
+        }
+        if (!check_case<5>(n, ol, radius, opt, cov)) { printf("case %ld kind %d\n", c, kind); return 1; }
+    }
+    printf("ok cases=%ld lp3_needed=%ld speculative_checked=%ld overlapping_pairs=%ld forced_parallel_lines=%ld\n", cases, cov[0], cov[1], cov[2], cov[3]);
+    return 0;
+}
