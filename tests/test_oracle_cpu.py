@@ -222,3 +222,31 @@ def test_python_loop_restatement_reproduces_reference(name):
         assert t == float(c['global_time'])
         r, _ = scene_arrays(c['final'])
         assert rxy == (r[0], r[1])
+
+
+@pytest.mark.parametrize('N', [1, 2, 5, 9, 10, 12])
+def test_rvo2_shim_vs_batched_oracle_random_crowds(oracle, N):
+    """Two code paths of the oracle against each other on tight random crowds (overlapping agents -> the one-time-step
+    branch, infeasible LPs -> lp3): the PyRVOSimulator shim (full doStep of every agent, kd-tree) and the batched env
+    oracle's per-agent solve must give the robot the same velocity, bit for bit."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle', 'shims'))
+    import rvo2
+    rng = np.random.RandomState(100 + N)
+    for trial in range(60):
+        spread = rng.choice([0.8, 2.0, 5.0])
+        st = oracle.HostState(1, N)
+        st.h_pos[0] = rng.uniform(-spread, spread, (N, 2)); st.h_vel[0] = rng.uniform(-1, 1, (N, 2)).astype(np.float32)
+        st.h_attr[0, :, 0] = rng.uniform(0.2, 0.5, N); st.h_attr[0, :, 1] = 1.0
+        st.r_pos[0] = rng.uniform(-spread, spread, 2); st.r_vel[0] = rng.uniform(-1, 1, 2).astype(np.float32)
+        st.r_goal[0] = rng.uniform(-6, 6, 2); st.r_attr[0] = (rng.uniform(0.2, 0.5), rng.uniform(0.5, 1.5))
+        act = oracle.orca_act(oracle.default_params(), st)[0]
+        sim = rvo2.PyRVOSimulator(0.25, 10, 10, 5, 5, 0.3, 1)
+        sim.addAgent(tuple(st.r_pos[0]), 10, 10, 5, 5, st.r_attr[0, 0] + 0.01 + 0, st.r_attr[0, 1], tuple(st.r_vel[0]))
+        for i in range(N):
+            sim.addAgent(tuple(st.h_pos[0, i]), 10, 10, 5, 5, st.h_attr[0, i, 0] + 0.01 + 0, 1, tuple(st.h_vel[0, i]))
+            sim.setAgentPrefVelocity(i + 1, (0, 0))
+        g = st.r_goal[0] - st.r_pos[0]
+        speed = np.linalg.norm(g)
+        sim.setAgentPrefVelocity(0, tuple(g / speed if speed > 1 else g))
+        sim.doStep()
+        assert sim.getAgentVelocity(0) == (act[0], act[1]), (N, trial)
