@@ -43,24 +43,25 @@ __device__ __forceinline__ int ar_decide(const StepArgs &A, int e, uint8_t s, bo
     return 0;
 }
 // Human lane a of env e: copy the prefetched scene into the live state (agent.py:47-58 set(px,py,gx,gy,0,0,...)).
+// The generator published the slot with (data, __threadfence, flag); the flag was read volatile at kernel start, the data
+// is read here with ld.global.cg (L2 = coherence point, no stale L1 line possible), so no reader-side fence is needed.
+__device__ __forceinline__ double2 ld2_cg(const double *p, size_t i) { return __ldcg(reinterpret_cast<const double2 *>(p) + i); }
 __device__ __forceinline__ void ar_install_human(const StepArgs &A, int e, int N, int a)
 {
-    __threadfence();                                           // the slot was published with a fence; read after the flag
     const size_t i = (size_t)e * N + a;
-    st2(A.st.h_pos, i, ld2(A.ar.n_h_pos, i)); st2(A.st.h_vel, i, make_double2(0, 0));
-    st2(A.st.h_goal, i, ld2(A.ar.n_h_goal, i)); st2(A.st.h_attr, i, ld2(A.ar.n_h_attr, i));
+    st2(A.st.h_pos, i, ld2_cg(A.ar.n_h_pos, i)); st2(A.st.h_vel, i, make_double2(0, 0));
+    st2(A.st.h_goal, i, ld2_cg(A.ar.n_h_goal, i)); st2(A.st.h_attr, i, ld2_cg(A.ar.n_h_attr, i));
 }
 // Robot lane of env e: crowd_sim.py:262,274 (global_time = 0, robot.set(0,-R,0,R,0,0,pi/2)) + fresh episode accumulators.
 __device__ __forceinline__ void ar_install_robot(const StepArgs &A, int e)
 {
-    __threadfence();
     st2(A.st.r_pos, e, make_double2(0.0, -A.ar.circle_radius)); st2(A.st.r_goal, e, make_double2(0.0, A.ar.circle_radius));
     st2(A.st.r_vel, e, make_double2(0, 0)); st2(A.st.r_attr, e, make_double2(A.ar.robot_radius, A.ar.robot_v_pref));
     if (A.st.r_theta) A.st.r_theta[e] = CS_PI / 2;
     A.st.g_time[e] = 0.0;
     if (A.has_ep) {
         A.ep.ep_steps[e] = 0; A.ep.ep_return[e] = 0.0; A.ep.ep_too_close[e] = 0; A.ep.ep_min_dist_sum[e] = 0.0;
-        A.ep.ep_case[e] = A.ar.n_case[e];
+        A.ep.ep_case[e] = __ldcg(A.ar.n_case + e);
     }
     A.st.active[e] = 1; A.ar.want[e] = 0;
 }
