@@ -38,6 +38,9 @@ def parse():
     ap.add_argument('--humans', type=int, default=5)
     ap.add_argument('--pools', type=int, default=0, help='independent batches rotated through (0 = enough to exceed L2)')
     ap.add_argument('--rule', default='circle_crossing')
+    ap.add_argument('--streams', type=int, default=8, help='independent env batches stepped concurrently (CUDA streams inside the timed graph)')
+    ap.add_argument('--prefetch-every', type=int, default=4, help='scene-prefetch launch for a batch on every n-th visit of that batch')
+    ap.add_argument('--e2e-batches', type=int, default=16, help='independent env batches kept in flight by the e2e leg')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-python-loop', action='store_true', help='reference arm: skip the reference-shaped Python loop timing')
     ap.add_argument('--no-scale', action='store_true', help='skip the supplementary 1 Mi-env launch measurement')
@@ -258,29 +261,44 @@ def run_ours(args):
     # only has to finish before the same batch is stepped again). The whole timed region is ONE CUDA graph of K steps:
     # Python/ctypes launch overhead (~20 us per call) would otherwise dominate a 4096-env step.
     main = torch.cuda.Stream(device=dev)
-    sides = [torch.cuda.Stream(device=dev) for _ in range(4)]
+    LANES = max(1, min(args.streams, pools))
+    lanes = [torch.cuda.Stream(device=dev) for _ in range(LANES)]
+    sides = [torch.cuda.Stream(device=dev) for _ in range(max(4, LANES))]
     it = 0
+    n_prefetch = 0
 
-    def capture(n_steps, with_prefetch=True, step_fn=None):
-        nonlocal it
+    def capture(n_steps, with_prefetch=True, step_fn=None, n_lanes=None):
+        """One CUDA graph of n_steps bench steps. Batch p is always stepped on lane (stream) p % n_lanes: the steps of one
+        batch stay ordered, steps of different (independent) batches may overlap on the device when n_lanes > 1."""
+        nonlocal it, n_prefetch
+        n_prefetch = 0
+        n_lanes = n_lanes or LANES
         g = torch.cuda.CUDAGraph()
         pending = {}                                   # pool -> event of its last prefetch inside this capture
         with torch.cuda.graph(g, stream=main):
+            fork = torch.cuda.Event(); fork.record(main)
+            for ls in lanes[:n_lanes]:
+                ls.wait_event(fork)
             for _ in range(n_steps):
                 p = it % pools; env = envs[p]; it += 1
-                if p in pending:
-                    main.wait_event(pending.pop(p))
-                (step_fn or (lambda e: e.step()))(env)
-                if with_prefetch:
-                    ev = torch.cuda.Event(); ev.record(main)
-                    sd = sides[p % len(sides)]
-                    sd.wait_event(ev)
-                    with torch.cuda.stream(sd):
-                        env.prefetch()
-                        done = torch.cuda.Event(); done.record(sd)
-                    pending[p] = done
-            for ev in pending.values():                # join the side branches
+                ls = lanes[p % n_lanes]
+                with torch.cuda.stream(ls):
+                    if p in pending:
+                        ls.wait_event(pending.pop(p))
+                    (step_fn or (lambda e: e.step()))(env)
+                    if with_prefetch and ((it - 1) // pools) % args.prefetch_every == 0:
+                        n_prefetch += 1
+                        ev = torch.cuda.Event(); ev.record(ls)
+                        sd = sides[p % len(sides)]
+                        sd.wait_event(ev)
+                        with torch.cuda.stream(sd):
+                            env.prefetch()
+                            done = torch.cuda.Event(); done.record(sd)
+                        pending[p] = done
+            for ev in pending.values():                # join the side branches and the lanes
                 main.wait_event(ev)
+            for ls in lanes[:n_lanes]:
+                ev = torch.cuda.Event(); ev.record(ls); main.wait_event(ev)
         return g
     with torch.cuda.stream(main):
         for _ in range(3):
@@ -288,10 +306,21 @@ def run_ours(args):
     torch.cuda.synchronize()
     g_warm = capture(max(W, 3))
     g_timed = capture(K)
+    timed_prefetches = n_prefetch
+
+    def env_steps_done():
+        """env-steps actually performed so far on this rank (finished episodes + episodes in progress): an env whose next
+        scene is not ready when its episode ends is parked until the refill arrives and performs no env-step meanwhile."""
+        tot = 0
+        for env in envs:
+            n = int(min(env._case_counter.item(), env.k_total))
+            tot += int(env.episodes.res_steps[:n].sum().item()) + int((env.episodes.ep_steps * env.state.active.to(torch.int32)).sum().item())
+        return tot
     sampler = ClockSampler(local)
     with torch.cuda.stream(main):
         g_warm.replay()
     barrier()
+    steps_before = env_steps_done()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.mark_start()
     with torch.cuda.stream(main):
@@ -300,14 +329,18 @@ def run_ours(args):
         e1.record()
     barrier()
     sampler.mark_stop()
-    launches = 2 * K
+    launches = K + timed_prefetches
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
+    live_steps = env_steps_done() - steps_before             # counted on device by the step kernel itself
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([live_steps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     ms_max = float(t.item())
-    value = world * B * K / (ms_max * 1e-3)
+    live_total = int(cnt.item())
+    value = live_total / (ms_max * 1e-3)                     # == world * B * K / time unless envs were parked
 
     # ---- the path's single collective: gather of episode statistics (terminal-class counts + env-steps of all finished
     # episodes of every rank) to rank 0 ----
@@ -332,6 +365,24 @@ def run_ours(args):
                 'note': 'all episodes finished so far on all ranks (gathered with one NCCL all_gather when n_gpus > 1); reference '
                         '500-case test suite: 0.43 / 0.57 / 0.006'}
 
+    # ---- the same bench step with ONE batch in flight (every step launch waits for the previous one): reported next to
+    # `value`, which keeps `--streams` independent batches in flight ----
+    single = None
+    if LANES > 1:
+        Ks = max(pools, K // 4)
+        g_single = capture(Ks, n_lanes=1)
+        barrier()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(main):
+            q0.record(); g_single.replay(); q1.record()
+        barrier()
+        tq = torch.tensor([q0.elapsed_time(q1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tq, op=dist.ReduceOp.MAX)
+        single = {'value': world * B * Ks / (float(tq.item()) * 1e-3), 'unit': 'env-steps/s', 'steps': Ks, 'ms_per_step': float(tq.item()) / Ks,
+                  'note': 'one 4096-env batch in flight at a time (single stream), nominal env-step count'}
+        del g_single
+
     # ---- roofline of the dominant kernel (the step kernel): a graph of one step launch per pool, no resets in between,
     # replayed R times; CUDA events on the launching stream; per-launch duration = elapsed / (R * pools). The pools
     # rotate, so each launch reads its state from HBM, not L2. ----
@@ -340,7 +391,7 @@ def run_ours(args):
         env.episodes = None; env.autoreset = None
         env.step()
         env.episodes, env.autoreset = ep, ar
-    g_step = capture(pools, with_prefetch=False, step_fn=step_only)
+    g_step = capture(pools, with_prefetch=False, step_fn=step_only, n_lanes=1)
     with torch.cuda.stream(main):
         g_step.replay()
     torch.cuda.synchronize()
@@ -363,7 +414,10 @@ def run_ours(args):
     roofline = {'bound': 'hbm', 'kernel': 'cs::step_flat_kernel' if N <= 5 else 'cs::step_kernel', 'achieved': achieved, 'peak': peak,
                 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': B * bytes_per_env, 'avg_launch_us': 1e3 * k_avg,
-                'how': 'CUDA events around %d replays of a graph of %d back-to-back step launches (one per rotating batch)' % (R, pools)}
+                'how': 'CUDA events around %d replays of a single-stream graph of %d back-to-back step launches (one per rotating batch)' % (R, pools),
+                'timed_region_GBps': (live_total / world) * bytes_per_env / (ms_max * 1e-3) / 1e9,
+                'timed_region_frac': (live_total / world) * bytes_per_env / (ms_max * 1e-3) / 1e9 / peak,
+                'timed_region_note': 'algorithmic bytes of all steps of the timed region / its duration, with %d independent batches in flight' % LANES}
 
     # ---- supplementary: the same step kernel when the batch fills the chip (1 Mi envs in ONE launch, state = 665 MB) ----
     scale = None
@@ -392,27 +446,45 @@ def run_ours(args):
     # ---- e2e: the public host-facing API (HostStepper.step): pinned HOST buffers in and out every step. The robot is
     # driven from the host like the reference's Explorer loop does it: action up, obs/reward/done/info (+ the robot's
     # next ORCA decision) down, host waits for the results before the next step. ----
+    import numpy as np
     from crowdnav_b200.batched import HostStepper
-    env = envs[0]
-    env.reset_seeds(rule=args.rule, use_queue=True)          # fresh scenes (the step-only pass ran past terminal states)
-    env.set_robot_policy('external_xy')
-    stepper = HostStepper(env, next_orca_action=True)
-    stepper.step()
-    for _ in range(5):
-        stepper.h_action.copy_(stepper.h_next_action); stepper.step()
-    barrier()
+    P = max(1, min(pools, args.e2e_batches))
+    steppers = []
+    for env in envs[:P]:
+        env.reset_seeds(rule=args.rule, use_queue=True)      # fresh scenes (the step-only pass ran past terminal states)
+        env.set_robot_policy('external_xy')
+        steppers.append(HostStepper(env, next_orca_action=True))
+    for st in steppers:
+        st.step()
+        for _ in range(5):
+            st.h_action.copy_(st.h_next_action); st.step()
     ke = min(K, 400)
-    t0 = time.perf_counter()
-    for _ in range(ke):
-        stepper.h_action.copy_(stepper.h_next_action)      # host-side "policy": apply the decision the device computed
-        stepper.step()
-    e2e_dt = time.perf_counter() - t0
-    t = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * ke / float(t.item())
+
+    def e2e_rate(group):
+        """Round-robin over the batches in `group`; each visit = wait for the batch's previous step (results in host
+        memory), host-side "policy" (apply the decision the device computed), enqueue its next step."""
+        for st in group:
+            st.launch()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            for st in group:
+                st.wait()
+                np.copyto(st.np_action, st.np_next_action)
+                st.launch()
+        for st in group:
+            st.wait()
+        dt_ = time.perf_counter() - t0
+        t = torch.tensor([dt_], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return world * B * ke * len(group) / float(t.item())
+
+    e2e_single = e2e_rate(steppers[:1])                      # one batch, host blocks on every step (the reference's loop shape)
+    e2e_value = e2e_rate(steppers) if P > 1 else e2e_single  # P independent batches in flight
+    stepper = steppers[0]
     h2d, d2h = stepper.h2d_bytes, stepper.d2h_bytes
-    launches_note = 'timed region: %d step + %d scene-prefetch kernel launches (one CUDA graph, prefetch on side streams)' % (K, K)
+    launches_note = 'timed region: %d step + %d scene-prefetch kernel launches (one CUDA graph, prefetch on side streams, every %d-th visit of a batch)' % (K, timed_prefetches, args.prefetch_every)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -426,11 +498,15 @@ def run_ours(args):
                 'dtype': 'f64 state + f32 ORCA solver', 'data': 'synthetic',
                 'config': {'workload': '%d batched envs x %d ORCA humans, %s, ORCA robot (invisible), auto-reset, per GPU' % (B, N, args.rule),
                            'envs_per_gpu': B, 'humans': N, 'l2': 'inputs larger than L2: %d rotating independent batches = %.0f MB of state' % (pools, pools * B * bytes_per_env / 1e6),
+                           'batches_in_flight': LANES,
                            'parallelism': 'independent envs sharded over %d GPU(s), no data-path collective' % world},
+                'env_steps': {'performed': live_total, 'nominal': world * B * K,
+                              'note': 'value = performed / time; performed is counted by the step kernel (episode step counters), nominal = envs x steps; they differ only if envs waited for a scene refill'},
                 'clocks': clocks, 'gpu_launches': int(launches), 'gpu_launches_note': launches_note,
                 'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                        'steps': ke, 'note': 'HostStepper.step(): pinned host buffers <-> device every step (one graph replay + stream sync per step); robot action uploaded, obs/reward/done/info/next ORCA action downloaded'},
-                'episodes': episodes, 'roofline': roofline, 'scale': scale, 'cpu_baseline': cpu}
+                        'steps': ke, 'batches_in_flight': P, 'single_batch_blocking': e2e_single,
+                        'note': 'HostStepper.launch()/wait() round-robin over %d independent 4096-env batches: per batch-step a pinned host action buffer goes up and obs/reward/done/info/next ORCA action come down (byte counts are per batch-step), the host waits for a batch\'s results before it feeds that batch again; single_batch_blocking = one batch, host blocks on every step' % P},
+                'single_stream': single, 'episodes': episodes, 'roofline': roofline, 'scale': scale, 'cpu_baseline': cpu}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -7,7 +7,7 @@ for its CPU library. No torch types cross the boundary.
 import ctypes as C
 import os
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_HUMANS = 63
 MAX_NEIGHBORS = 10
 
@@ -85,7 +85,8 @@ def declare(lib, prefix='crowdsim_', with_stream=True):
     return lib
 
 
-EXPORTS = ('crowdsim_abi_version', 'crowdsim_device_check', 'crowdsim_launch_count', 'crowdsim_debug_force_generic', 'crowdsim_step',
+EXPORTS = ('crowdsim_abi_version', 'crowdsim_device_check', 'crowdsim_launch_count', 'crowdsim_debug_force_generic', 'crowdsim_graph_launch',
+           'crowdsim_event_wait', 'crowdsim_step',
            'crowdsim_orca_act', 'crowdsim_reset', 'crowdsim_prefetch_scenes', 'crowdsim_pack_joint', 'crowdsim_lookahead_pack')
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc', 'libcrowdsim_b200.so')
@@ -111,6 +112,10 @@ def load():
         lib.crowdsim_launch_count.restype = C.c_ulonglong
         lib.crowdsim_debug_force_generic.argtypes = [C.c_int]
         lib.crowdsim_debug_force_generic.restype = None
+        lib.crowdsim_graph_launch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.crowdsim_graph_launch.restype = C.c_int
+        lib.crowdsim_event_wait.argtypes = [C.c_void_p]
+        lib.crowdsim_event_wait.restype = C.c_int
         declare(lib)
         if lib.crowdsim_abi_version() != ABI_VERSION:
             raise CudaLibraryMissing('ABI version mismatch: library %d, python %d'

@@ -365,6 +365,7 @@ class HostStepper(object):
         self.h_done, self.h_info, self.h_action_out, self.h_next_action = hs['done'], hs['info'], hs['action_out'], hs['next_action']
         self.stream = torch.cuda.Stream(device=dev)
         self.side = torch.cuda.Stream(device=dev)
+        self.done_event = torch.cuda.Event()
         self.h2d_bytes = self.h_action.numel() * 8
         self.d2h_bytes = hs.nbytes
         self.kernels_per_step = 1 + (1 if env.autoreset is not None else 0) + (1 if next_orca_action else 0)
@@ -392,12 +393,34 @@ class HostStepper(object):
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, stream=self.stream):
             body()
+        self._lib = _abi.load()
+        self._exec = self.graph.raw_cuda_graph_exec()
+        self.done_event.record(self.stream)            # creates the underlying cudaEvent_t
+        self._event_h = self.done_event.cuda_event
+        self._stream_h = self.stream.cuda_stream
+        self._result = ((self.h_pos, self.h_vel), self.h_reward, self.h_done, self.h_info)
+        self.np_action, self.np_next_action = self.h_action.numpy(), self.h_next_action.numpy()
 
     def step(self):
-        with torch.cuda.stream(self.stream):
-            self.graph.replay()
-        self.stream.synchronize()
-        return (self.h_pos, self.h_vel), self.h_reward, self.h_done, self.h_info
+        self.launch()
+        return self.wait()
+
+    # Split form of step() for callers that keep several independent env batches in flight (one HostStepper per batch,
+    # each with its own streams and pinned buffers): launch() enqueues the step of this batch and returns at once, wait()
+    # blocks until its results are in the host buffers. The uploads/downloads of one batch then overlap the kernels of the
+    # others; every batch still pays its own H2D action copy and D2H result copy on every step.
+    # Both go straight to the library (crowdsim_graph_launch / crowdsim_event_wait on the raw graph-exec, stream and
+    # event handles): ~3 us of interpreter time per call instead of ~12 us through torch's stream context + replay().
+    def launch(self):
+        rc = self._lib.crowdsim_graph_launch(self._exec, self._stream_h, self._event_h)
+        if rc:
+            _abi.check(rc, 'crowdsim_graph_launch')
+
+    def wait(self):
+        rc = self._lib.crowdsim_event_wait(self._event_h)
+        if rc:
+            _abi.check(rc, 'crowdsim_event_wait')
+        return self._result
 
 
 def default_config(human_num=5, test_sim='circle_crossing', train_val_sim='circle_crossing', robot_visible=False,

@@ -31,10 +31,13 @@ namespace cs {
 // attribute latency); the library only instantiates the full kernel (STAGE = 99).
 // Register budget: asking for 6 resident blocks per SM (<= 80 registers, a few bytes of spill) is neutral at 4096 envs and
 // 9 % faster at 65 k .. 1 M envs than the unconstrained 90-register build (scripts/latency_probe.cu, -DCS_FLAT_MINBLOCKS=1/6/8).
+#ifndef CS_FLAT_WARP_LP3
+#define CS_FLAT_WARP_LP3 0
+#endif
 #ifndef CS_FLAT_MINBLOCKS
 #define CS_FLAT_MINBLOCKS 6
 #endif
-template <int N, int STAGE = 99>
+template <int N, int STAGE = 99, bool WARPQ = (CS_FLAT_WARP_LP3 != 0)>
 __global__ void __launch_bounds__(128, CS_FLAT_MINBLOCKS) step_flat_kernel(const __grid_constant__ StepArgs A)
 {
     if constexpr (STAGE == 0) return;
@@ -59,7 +62,8 @@ __global__ void __launch_bounds__(128, CS_FLAT_MINBLOCKS) step_flat_kernel(const
 
     // ---- all global loads of the step are issued up front, unconditionally for valid envs, so that they overlap into ONE
     // DRAM round trip (active flag -> state -> episode accumulators / slot state used to be dependent ones) ----
-    double2 pos = make_double2(0, 0), vel = pos, goal = pos, attr = make_double2(0.3, 1.0);
+    // (idle lanes get a goal 5 m away: a zero goal vector would drag the warp through the f64 sqrt / division slow paths)
+    double2 pos = make_double2(0, 0), vel = pos, goal = make_double2(3, 4), attr = make_double2(0.3, 1.0);
     double theta = 0, gtime = 0; double2 ext = make_double2(0, 0);
     uint8_t act_flag = 1, slot_state = 0, want_flag = 0;
     int ep_t = 0, ep_tc = 0, ep_c = -1; double ep_ret = 0, ep_mds = 0;
@@ -159,52 +163,102 @@ __global__ void __launch_bounds__(128, CS_FLAT_MINBLOCKS) step_flat_kernel(const
         return;
     }
     const bool need3 = solves && fail < nl;
-    __syncthreads();                                         // s_qcount = 0 visible
-    int slot = -1;
-    if (need3) {
-        slot = atomicAdd(&s_qcount, 1);
-        #pragma unroll
-        for (int kk = 0; kk < M; ++kk) {
-            s_q[4 * kk + 0][slot] = R.p[kk].x; s_q[4 * kk + 1][slot] = R.p[kk].y;
-            s_q[4 * kk + 2][slot] = R.d[kk].x; s_q[4 * kk + 3][slot] = R.d[kk].y;
-        }
-        s_q[4 * M + 0][slot] = __int_as_float(nl); s_q[4 * M + 1][slot] = __int_as_float(fail);
-        s_q[4 * M + 2][slot] = max_speed; s_q[4 * M + 3][slot] = nv.x; s_q[4 * M + 4][slot] = nv.y;
-    }
-    if (__syncthreads_or(need3 ? 1 : 0)) {
-        const int cnt = s_qcount;
-        constexpr int IPP = T / SUB;                         // items per pass
-        for (int base = 0; base < cnt; base += IPP) {
-            const int item = base + tid / SUB, i = tid % SUB + 1;
-            const bool mine = (tid < IPP * SUB) && item < cnt;
-            if (mine) {
-                const Lines Lq = { &s_q[0][item], T };
-                const int qn = __float_as_int(s_q[4 * M + 0][item]);
-                bool ok = false; V2 r2 = mk(0.f, 0.f);
-                if (M > 1 && i < qn) {
-                    // sequential shared-memory LP code (early exits): measured faster here than a register-resident
-                    // speculative version of the sub-problem (LP3 stage 3.5 vs 4.5 us at 4096 envs)
-                    const Lines Pq = { &s_p[0][tid], T };
-                    ok = lp3_subproblem(Lq, i, s_q[4 * M + 2][item], Pq, r2);
+    if constexpr (WARPQ) {
+        // warp-level queue: no block barrier; every warp runs the sub-problems of its own solves
+        const unsigned m3 = __ballot_sync(CS_FULL, need3);
+        if (m3) {
+            const int wbase = wib * 32;
+            const int cnt = __popc(m3);
+            const int slot = wbase + __popc(m3 & ((1u << lane) - 1u));
+            if (need3) {
+                #pragma unroll
+                for (int kk = 0; kk < M; ++kk) {
+                    s_q[4 * kk + 0][slot] = R.p[kk].x; s_q[4 * kk + 1][slot] = R.p[kk].y;
+                    s_q[4 * kk + 2][slot] = R.d[kk].x; s_q[4 * kk + 3][slot] = R.d[kk].y;
                 }
-                s_r2[0][tid] = r2.x; s_r2[1][tid] = r2.y; s_r2[2][tid] = ok ? 1.0f : 0.0f;
+                s_q[4 * M + 0][slot] = __int_as_float(nl); s_q[4 * M + 1][slot] = __int_as_float(fail);
+                s_q[4 * M + 2][slot] = max_speed; s_q[4 * M + 3][slot] = nv.x; s_q[4 * M + 4][slot] = nv.y;
             }
-            __syncthreads();
-            if (mine && i == 1) {                            // the item's first lane runs linearProgram3's outer scan
-                const Lines Lq = { &s_q[0][item], T };
-                const int qn = __float_as_int(s_q[4 * M + 0][item]), qf = __float_as_int(s_q[4 * M + 1][item]);
-                const float qr = s_q[4 * M + 2][item];
-                V2 res = mk(s_q[4 * M + 3][item], s_q[4 * M + 4][item]);
-                lp3_outer_scan(Lq, qn, qf, qr, res, [&](int ii, V2 &r2) {
-                    const int src = tid + (ii - 1);               // lane of sub-problem ii of this item
-                    r2 = mk(s_r2[0][src], s_r2[1][src]);
-                    return s_r2[2][src] != 0.0f;
-                });
-                s_res[0][item] = res.x; s_res[1][item] = res.y;
+            __syncwarp();
+            constexpr int IPP = 32 / SUB;                        // items per pass
+            for (int base = 0; base < cnt; base += IPP) {
+                const int item = wbase + base + lane / SUB, i = lane % SUB + 1;
+                const bool mine = (lane < IPP * SUB) && (base + lane / SUB) < cnt;
+                if (mine) {
+                    const Lines Lq = { &s_q[0][item], T };
+                    const int qn = __float_as_int(s_q[4 * M + 0][item]);
+                    bool ok = false; V2 r2 = mk(0.f, 0.f);
+                    if (M > 1 && i < qn) {
+                        const Lines Pq = { &s_p[0][tid], T };
+                        ok = lp3_subproblem(Lq, i, s_q[4 * M + 2][item], Pq, r2);
+                    }
+                    s_r2[0][tid] = r2.x; s_r2[1][tid] = r2.y; s_r2[2][tid] = ok ? 1.0f : 0.0f;
+                }
+                __syncwarp();
+                if (mine && i == 1) {
+                    const Lines Lq = { &s_q[0][item], T };
+                    const int qn = __float_as_int(s_q[4 * M + 0][item]), qf = __float_as_int(s_q[4 * M + 1][item]);
+                    const float qr = s_q[4 * M + 2][item];
+                    V2 res = mk(s_q[4 * M + 3][item], s_q[4 * M + 4][item]);
+                    lp3_outer_scan(Lq, qn, qf, qr, res, [&](int ii, V2 &r2) {
+                        const int src = tid + (ii - 1);
+                        r2 = mk(s_r2[0][src], s_r2[1][src]);
+                        return s_r2[2][src] != 0.0f;
+                    });
+                    s_res[0][item] = res.x; s_res[1][item] = res.y;
+                }
+                __syncwarp();
             }
-            __syncthreads();
+            if (need3) nv = mk(s_res[0][slot], s_res[1][slot]);
         }
-        if (need3) nv = mk(s_res[0][slot], s_res[1][slot]);
+    } else {
+        __syncthreads();                                         // s_qcount = 0 visible
+        int slot = -1;
+        if (need3) {
+            slot = atomicAdd(&s_qcount, 1);
+            #pragma unroll
+            for (int kk = 0; kk < M; ++kk) {
+                s_q[4 * kk + 0][slot] = R.p[kk].x; s_q[4 * kk + 1][slot] = R.p[kk].y;
+                s_q[4 * kk + 2][slot] = R.d[kk].x; s_q[4 * kk + 3][slot] = R.d[kk].y;
+            }
+            s_q[4 * M + 0][slot] = __int_as_float(nl); s_q[4 * M + 1][slot] = __int_as_float(fail);
+            s_q[4 * M + 2][slot] = max_speed; s_q[4 * M + 3][slot] = nv.x; s_q[4 * M + 4][slot] = nv.y;
+        }
+        if (__syncthreads_or(need3 ? 1 : 0)) {
+            const int cnt = s_qcount;
+            constexpr int IPP = T / SUB;                         // items per pass
+            for (int base = 0; base < cnt; base += IPP) {
+                const int item = base + tid / SUB, i = tid % SUB + 1;
+                const bool mine = (tid < IPP * SUB) && item < cnt;
+                if (mine) {
+                    const Lines Lq = { &s_q[0][item], T };
+                    const int qn = __float_as_int(s_q[4 * M + 0][item]);
+                    bool ok = false; V2 r2 = mk(0.f, 0.f);
+                    if (M > 1 && i < qn) {
+                        // sequential shared-memory LP code (early exits): measured faster here than a register-resident
+                        // speculative version of the sub-problem (LP3 stage 3.5 vs 4.5 us at 4096 envs)
+                        const Lines Pq = { &s_p[0][tid], T };
+                        ok = lp3_subproblem(Lq, i, s_q[4 * M + 2][item], Pq, r2);
+                    }
+                    s_r2[0][tid] = r2.x; s_r2[1][tid] = r2.y; s_r2[2][tid] = ok ? 1.0f : 0.0f;
+                }
+                __syncthreads();
+                if (mine && i == 1) {                            // the item's first lane runs linearProgram3's outer scan
+                    const Lines Lq = { &s_q[0][item], T };
+                    const int qn = __float_as_int(s_q[4 * M + 0][item]), qf = __float_as_int(s_q[4 * M + 1][item]);
+                    const float qr = s_q[4 * M + 2][item];
+                    V2 res = mk(s_q[4 * M + 3][item], s_q[4 * M + 4][item]);
+                    lp3_outer_scan(Lq, qn, qf, qr, res, [&](int ii, V2 &r2) {
+                        const int src = tid + (ii - 1);               // lane of sub-problem ii of this item
+                        r2 = mk(s_r2[0][src], s_r2[1][src]);
+                        return s_r2[2][src] != 0.0f;
+                    });
+                    s_res[0][item] = res.x; s_res[1][item] = res.y;
+                }
+                __syncthreads();
+            }
+            if (need3) nv = mk(s_res[0][slot], s_res[1][slot]);
+        }
     }
 
     if (A.act_only) {                      // crowdsim_orca_act: the robot's ORCA decision only, nothing is mutated

@@ -245,13 +245,22 @@ static int launch(const crowdsim_params *prm, int B, int N, const crowdsim_state
         // small crowds: register-resident solver, 32 / (N + 1) whole envs per warp (step_flat.cuh)
         const int epb = 4 * (32 / (N + 1));
         const int blocks = (B + epb - 1) / epb;
+        // linearProgram3 queue: per warp when the launch leaves SMs mostly empty (latency-bound: no block barrier, 2-4 %
+        // faster at 1 k - 4 k envs), per block when the chip is full (issue-bound: one warp runs the pass for the whole block,
+        // 3-5 % faster at 64 k - 1 M envs). Measured with scripts/gpu_ab_lp3.sh.
+        static int n_sm = 0;
+        if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148; }
+        const bool warpq = blocks <= 3 * n_sm;
+        #define CS_FLAT_LAUNCH(NN) do { if (warpq) step_flat_kernel<NN, 99, true><<<blocks, 128, 0, stream>>>(A); \
+                                        else step_flat_kernel<NN, 99, false><<<blocks, 128, 0, stream>>>(A); } while (0)
         switch (N) {
-            case 1: step_flat_kernel<1><<<blocks, 128, 0, stream>>>(A); break;
-            case 2: step_flat_kernel<2><<<blocks, 128, 0, stream>>>(A); break;
-            case 3: step_flat_kernel<3><<<blocks, 128, 0, stream>>>(A); break;
-            case 4: step_flat_kernel<4><<<blocks, 128, 0, stream>>>(A); break;
-            default: step_flat_kernel<5><<<blocks, 128, 0, stream>>>(A); break;
+            case 1: CS_FLAT_LAUNCH(1); break;
+            case 2: CS_FLAT_LAUNCH(2); break;
+            case 3: CS_FLAT_LAUNCH(3); break;
+            case 4: CS_FLAT_LAUNCH(4); break;
+            default: CS_FLAT_LAUNCH(5); break;
         }
+        #undef CS_FLAT_LAUNCH
         ++g_launches;
         return (int)cudaGetLastError();
     }
@@ -280,6 +289,20 @@ extern "C" int crowdsim_orca_act(const crowdsim_params *prm, int B, int N, const
 {
     crowdsim_step_io io; memset(&io, 0, sizeof(io)); io.action_out = action_out;
     return cs::launch(prm, B, N, st, &io, nullptr, nullptr, 1, (cudaStream_t)stream);
+}
+
+extern "C" int crowdsim_graph_launch(void *graph_exec, void *stream, void *done_event)
+{
+    if (!graph_exec) return CROWDSIM_EINVAL;
+    cudaError_t e = cudaGraphLaunch((cudaGraphExec_t)graph_exec, (cudaStream_t)stream);
+    if (e == cudaSuccess && done_event) e = cudaEventRecord((cudaEvent_t)done_event, (cudaStream_t)stream);
+    return (int)e;
+}
+
+extern "C" int crowdsim_event_wait(void *event)
+{
+    if (!event) return CROWDSIM_EINVAL;
+    return (int)cudaEventSynchronize((cudaEvent_t)event);
 }
 
 extern "C" void crowdsim_debug_force_generic(int on) { cs::g_force_generic = on; }

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define CROWDSIM_ABI_VERSION 2
+#define CROWDSIM_ABI_VERSION 3
 
 /* error codes */
 #define CROWDSIM_OK            0
@@ -184,6 +184,13 @@ unsigned long long crowdsim_launch_count(void);
 /* Test hook: 1 = use the generic one-thread-per-agent step kernel for every N (default 0: N <= 5 uses the
  * register-resident small-crowd kernel). Both are held to the same bit-exact parity bar. */
 void crowdsim_debug_force_generic(int on);
+
+/* Host plumbing for callers that keep several env batches in flight from an interpreter (batched.HostStepper.launch /
+ * wait; the reference's loop blocks in env.step, crowd_nav/utils/explorer.py:42-43): replay a captured CUDA graph
+ * (cudaGraphExec_t) of one batch's step on `stream` and record `done_event` (cudaEvent_t, may be NULL) behind it / block
+ * until that event has completed. No kernel of this library is launched directly by these two calls. */
+int crowdsim_graph_launch(void *graph_exec, void *stream, void *done_event);
+int crowdsim_event_wait(void *event);
 
 /* One lockstep env-step for B envs. `ep` and `ar` may be NULL. */
 int crowdsim_step(const crowdsim_params *prm, int B, int N, crowdsim_state *st, crowdsim_step_io *io,

@@ -72,6 +72,7 @@ def test_argument_validation_without_gpu(lib):
     assert lib.crowdsim_pack_joint(1, 5, C.byref(st), 0, None, None) == -1
     assert lib.crowdsim_lookahead_pack(C.byref(prm), 1, 5, C.byref(st), None, 81, 0, None, None, None) == -1
     assert lib.crowdsim_orca_act(C.byref(prm), 1, 5, C.byref(st), None, None) == -1
+    assert lib.crowdsim_graph_launch(None, None, None) == -1 and lib.crowdsim_event_wait(None) == -1
     assert lib.crowdsim_launch_count() == 0          # nothing was launched by rejected calls
 
 

@@ -117,6 +117,24 @@ def test_step_random_scenes_bit_exact(cuda_env, oracle, N, vis, policy, generic)
             _assert_io_equal(env, io, what='N=%d step %d' % (N, t))
 
 
+@pytest.mark.parametrize('N,vis', [(5, 0), (5, 1), (3, 1), (2, 0)])
+def test_step_random_scenes_full_chip_grid(cuda_env, oracle, N, vis):
+    """Launches of more than 3 blocks per SM take the block-compacted linearProgram3 queue of the small-crowd kernel
+    (smaller ones the per-warp queue, step_kernel.cu: launch): same dense random scenes, 20 000 envs, 6 steps, equality."""
+    B = 20000
+    host = _random_host_state(oracle, B, N, seed=900 + N)
+    env = cuda_env(B, N, robot_visible=bool(vis), robot_policy='orca')
+    env.state.load_host(host)
+    prm = oracle.default_params(robot_visible=vis)
+    io = oracle.HostStepIO(B)
+    for t in range(6):
+        env.step()
+        oracle.step(prm, host, io)
+        torch.cuda.synchronize()
+        _assert_state_equal(env, host, what='N=%d step %d' % (N, t))
+        _assert_io_equal(env, io, what='N=%d step %d' % (N, t))
+
+
 @pytest.mark.parametrize('generic', [0, 1])
 @pytest.mark.parametrize('name', sorted(SUITES))
 def test_full_suites_from_reference_scenes(cuda_env, oracle, name, generic):

@@ -149,3 +149,34 @@ def test_host_stepper_matches_oracle(cuda_env, oracle):
         assert np.array_equal(rew.numpy(), io.reward) and np.array_equal(done.numpy(), io.done) and np.array_equal(info.numpy(), io.info)
         act = oracle.orca_act(oracle.default_params(), host)
         assert np.array_equal(stepper.h_next_action.numpy(), act), t
+
+
+def test_host_stepper_batches_in_flight(cuda_env, oracle):
+    """launch()/wait(): three independent env batches kept in flight on their own streams produce, batch for batch and
+    step for step, what the oracle produces for each of them alone."""
+    from crowdnav_b200.batched import HostStepper
+    from crowdnav_b200 import _abi
+    B, N, P = 200, 5, 3
+    prm_ext = oracle.default_params(robot_policy=_abi.ROBOT_EXTERNAL_XY)
+    hosts, ios, envs, steppers, acts = [], [], [], [], []
+    for q in range(P):
+        host = oracle.HostState(B, N); oracle.reset(host, np.arange(B) + 5000 + 1000 * q)
+        env = cuda_env(B, N, robot_policy='external_xy')
+        st = HostStepper(env, next_orca_action=True)
+        env.state.load_host(host)
+        hosts.append(host); ios.append(oracle.HostStepIO(B)); envs.append(env); steppers.append(st)
+        acts.append(oracle.orca_act(oracle.default_params(), host))
+    for q in range(P):
+        steppers[q].h_action.copy_(torch.from_numpy(acts[q])); steppers[q].launch()
+    for t in range(20):
+        for q in range(P):
+            (h_pos, h_vel), rew, done, info = steppers[q].wait()
+            ios[q].action[...] = acts[q]
+            oracle.step(prm_ext, hosts[q], ios[q])
+            assert np.array_equal(h_pos.numpy(), hosts[q].h_pos) and np.array_equal(h_vel.numpy(), hosts[q].h_vel), (t, q)
+            assert np.array_equal(rew.numpy(), ios[q].reward) and np.array_equal(info.numpy(), ios[q].info), (t, q)
+            acts[q] = oracle.orca_act(oracle.default_params(), hosts[q])
+            assert np.array_equal(steppers[q].h_next_action.numpy(), acts[q]), (t, q)
+            steppers[q].h_action.copy_(steppers[q].h_next_action); steppers[q].launch()
+    for q in range(P):
+        steppers[q].wait()
