@@ -89,7 +89,10 @@ EXPORTS = ('crowdsim_abi_version', 'crowdsim_device_check', 'crowdsim_launch_cou
            'crowdsim_event_wait', 'crowdsim_step',
            'crowdsim_orca_act', 'crowdsim_reset', 'crowdsim_prefetch_scenes', 'crowdsim_pack_joint', 'crowdsim_lookahead_pack')
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc', 'libcrowdsim_b200.so')
+# CROWDSIM_B200_LIB selects another build of the SAME library (A/B runs of kernel variants, scripts/gpu_variants.sh);
+# it is never a fallback: the named file must exist.
+LIB_PATH = os.environ.get('CROWDSIM_B200_LIB') or os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc',
+                                                               'libcrowdsim_b200.so')
 _lib = None
 
 

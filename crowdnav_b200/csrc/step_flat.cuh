@@ -31,6 +31,10 @@ namespace cs {
 // attribute latency); the library only instantiates the full kernel (STAGE = 99).
 // Register budget: asking for 6 resident blocks per SM (<= 80 registers, a few bytes of spill) is neutral at 4096 envs and
 // 9 % faster at 65 k .. 1 M envs than the unconstrained 90-register build (scripts/latency_probe.cu, -DCS_FLAT_MINBLOCKS=1/6/8).
+// Warps per block (block = CS_FLAT_WPB * 32 threads) and the resident-blocks hint that goes with it.
+#ifndef CS_FLAT_WPB
+#define CS_FLAT_WPB 4
+#endif
 #ifndef CS_FLAT_WARP_LP3
 #define CS_FLAT_WARP_LP3 0
 #endif
@@ -38,11 +42,11 @@ namespace cs {
 #define CS_FLAT_MINBLOCKS 6
 #endif
 template <int N, int STAGE = 99, bool WARPQ = (CS_FLAT_WARP_LP3 != 0)>
-__global__ void __launch_bounds__(128, CS_FLAT_MINBLOCKS) step_flat_kernel(const __grid_constant__ StepArgs A)
+__global__ void __launch_bounds__(32 * CS_FLAT_WPB, CS_FLAT_MINBLOCKS * 4 / CS_FLAT_WPB) step_flat_kernel(const __grid_constant__ StepArgs A)
 {
     if constexpr (STAGE == 0) return;
     using namespace orca;
-    constexpr int L = N + 1, M = N, EPW = 32 / L, WPB = 4, T = 32 * WPB;
+    constexpr int L = N + 1, M = N, EPW = 32 / L, WPB = CS_FLAT_WPB, T = 32 * WPB;
     constexpr int SUB = (M > 1) ? M - 1 : 1;                // lanes per queued lp3 item (sub-problems i = 1 .. M-1)
     constexpr int QF = 4 * M + 5;                           // floats per queued lp3 work item
     __shared__ float s_q[QF][T];                            // [field][slot]: lines of an item = orca::Lines(base = &s_q[0][slot], stride = T)

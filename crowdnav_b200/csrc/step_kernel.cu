@@ -243,16 +243,16 @@ static int launch(const crowdsim_params *prm, int B, int N, const crowdsim_state
     if (A.has_ar) A.ar = *ar; else memset(&A.ar, 0, sizeof(A.ar));
     if (N >= 1 && N <= 5 && !g_force_generic) {
         // small crowds: register-resident solver, 32 / (N + 1) whole envs per warp (step_flat.cuh)
-        const int epb = 4 * (32 / (N + 1));
+        const int epb = CS_FLAT_WPB * (32 / (N + 1));
         const int blocks = (B + epb - 1) / epb;
         // linearProgram3 queue: per warp when the launch leaves SMs mostly empty (latency-bound: no block barrier, 2-4 %
         // faster at 1 k - 4 k envs), per block when the chip is full (issue-bound: one warp runs the pass for the whole block,
         // 3-5 % faster at 64 k - 1 M envs). Measured with scripts/gpu_ab_lp3.sh.
         static int n_sm = 0;
         if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148; }
-        const bool warpq = blocks <= 3 * n_sm;
-        #define CS_FLAT_LAUNCH(NN) do { if (warpq) step_flat_kernel<NN, 99, true><<<blocks, 128, 0, stream>>>(A); \
-                                        else step_flat_kernel<NN, 99, false><<<blocks, 128, 0, stream>>>(A); } while (0)
+        const bool warpq = blocks * CS_FLAT_WPB <= 12 * n_sm;
+        #define CS_FLAT_LAUNCH(NN) do { if (warpq) step_flat_kernel<NN, 99, true><<<blocks, 32 * CS_FLAT_WPB, 0, stream>>>(A); \
+                                        else step_flat_kernel<NN, 99, false><<<blocks, 32 * CS_FLAT_WPB, 0, stream>>>(A); } while (0)
         switch (N) {
             case 1: CS_FLAT_LAUNCH(1); break;
             case 2: CS_FLAT_LAUNCH(2); break;

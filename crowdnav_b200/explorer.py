@@ -14,7 +14,7 @@ With update_memory=True the rollout also fills a memory.DeviceReplayMemory like 
 (explorer.py:92-125; imitation-learning returns or target-network bootstraps).
 
 Multi-GPU (torchrun, one process per GPU): the k cases are split into contiguous ranges per rank; there is no data-path
-collective; ONE gather of the per-case result rows (32 B per episode; NCCL on GPU tensors, gloo in the CPU tests) brings
+collective; ONE gather of the per-case result rows (48 B per episode: 6 float64 columns; NCCL on GPU tensors, gloo in the CPU tests) brings
 them to rank 0, which prints the log lines.
 """
 import logging
