@@ -14,7 +14,9 @@ MAX_NEIGHBORS = 10
 INFO_NOTHING, INFO_DANGER, INFO_REACHGOAL, INFO_COLLISION, INFO_TIMEOUT = 0, 1, 2, 3, 4
 ROBOT_EXTERNAL_XY, ROBOT_ORCA, ROBOT_EXTERNAL_ROT = 0, 1, 2
 RULE_CIRCLE, RULE_SQUARE = 0, 1
-RULES = {'circle_crossing': RULE_CIRCLE, 'square_crossing': RULE_SQUARE}
+RULE_MIXED = 2
+PARKED_X = 1.0e6                  # include/crowdsim_b200.h: CROWDSIM_PARKED_X
+RULES = {'circle_crossing': RULE_CIRCLE, 'square_crossing': RULE_SQUARE, 'mixed': RULE_MIXED}
 
 _dp, _u8p, _i32p, _u32p, _f32p = (C.POINTER(C.c_double), C.POINTER(C.c_uint8), C.POINTER(C.c_int32),
                                   C.POINTER(C.c_uint32), C.POINTER(C.c_float))
@@ -87,7 +89,8 @@ def declare(lib, prefix='crowdsim_', with_stream=True):
 
 EXPORTS = ('crowdsim_abi_version', 'crowdsim_device_check', 'crowdsim_launch_count', 'crowdsim_debug_force_generic', 'crowdsim_graph_launch',
            'crowdsim_event_wait', 'crowdsim_step',
-           'crowdsim_orca_act', 'crowdsim_reset', 'crowdsim_prefetch_scenes', 'crowdsim_pack_joint', 'crowdsim_lookahead_pack')
+           'crowdsim_orca_act', 'crowdsim_reset', 'crowdsim_prefetch_scenes', 'crowdsim_pack_joint', 'crowdsim_lookahead_pack',
+           'crowdsim_lookahead_humans', 'crowdsim_occupancy_maps')
 
 # CROWDSIM_B200_LIB selects another build of the SAME library (A/B runs of kernel variants, scripts/gpu_variants.sh);
 # it is never a fallback: the named file must exist.
@@ -119,6 +122,10 @@ def load():
         lib.crowdsim_graph_launch.restype = C.c_int
         lib.crowdsim_event_wait.argtypes = [C.c_void_p]
         lib.crowdsim_event_wait.restype = C.c_int
+        lib.crowdsim_lookahead_humans.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.POINTER(State), C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.crowdsim_lookahead_humans.restype = C.c_int
+        lib.crowdsim_occupancy_maps.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+        lib.crowdsim_occupancy_maps.restype = C.c_int
         declare(lib)
         if lib.crowdsim_abi_version() != ABI_VERSION:
             raise CudaLibraryMissing('ABI version mismatch: library %d, python %d'

@@ -344,6 +344,39 @@ class BatchedCrowdSim(object):
         return out_states, out_reward
 
 
+    def human_counts(self):
+        """Humans present per env [B] (int64). Differs from human_num only for scenes of rule `mixed` (crowd_sim.py:103-151),
+        whose unused human slots are parked at x >= CROWDSIM_PARKED_X (include/crowdsim_b200.h)."""
+        return (self.state.h_pos[:, :, 0] < _abi.PARKED_X / 2).sum(dim=1)
+
+    def lookahead_humans(self, out_pos=None, out_vel=None):
+        """The observation of env.onestep_lookahead (crowd_sim.py:414-416): the humans' next positions / velocities
+        [B][N][2] float64 under their own ORCA decisions; the state is not touched."""
+        if out_pos is None:
+            out_pos = torch.empty((self.B, self.human_num, 2), dtype=torch.float64, device=self.device)
+        if out_vel is None:
+            out_vel = torch.empty((self.B, self.human_num, 2), dtype=torch.float64, device=self.device)
+        prm = self.params(); st = self.state.struct()
+        rc = self.lib.crowdsim_lookahead_humans(C.byref(prm), self.B, self.human_num, C.byref(st), _ptr(out_pos), _ptr(out_vel),
+                                                self._stream())
+        _abi.check(rc, 'crowdsim_lookahead_humans')
+        return out_pos, out_vel
+
+    def occupancy_maps(self, h_pos=None, h_vel=None, cell_num=4, cell_size=1.0, om_channel_size=3, out=None):
+        """MultiHumanRL.build_occupancy_maps (multi_human_rl.py:109-163) for every env: [B][N][cell_num^2 * channels]
+        float32. Default input = the live human state; pass the output of lookahead_humans() for next-state maps."""
+        if self.human_num < 2:
+            raise ValueError('need at least one array to concatenate')      # what the reference's np.concatenate raises
+        h_pos = self.state.h_pos if h_pos is None else h_pos
+        h_vel = self.state.h_vel if h_vel is None else h_vel
+        if out is None:
+            out = torch.empty((self.B, self.human_num, cell_num * cell_num * om_channel_size), dtype=torch.float32, device=self.device)
+        rc = self.lib.crowdsim_occupancy_maps(self.B, self.human_num, _ptr(h_pos), _ptr(h_vel), int(cell_num), float(cell_size),
+                                              int(om_channel_size), _ptr(out), self._stream())
+        _abi.check(rc, 'crowdsim_occupancy_maps')
+        return out
+
+
 class HostStepper(object):
     """env.step() for callers that live on the host (the reference's calling convention: the policy hands a robot
     action to env.step and gets observation, reward, done, info back -- crowd_nav/utils/explorer.py:42-43).

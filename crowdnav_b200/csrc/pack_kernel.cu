@@ -170,6 +170,80 @@ __global__ void __launch_bounds__(256) lookahead_kernel(const __grid_constant__ 
     }
 }
 
+
+// ---- onestep_lookahead's observation (crowd_sim.py:414-416, agent.py:63-74): the humans' next observable states for the
+// CURRENT state, nothing mutated. Same staging and solver as the lookahead kernel. ----
+struct NextArgs { KParams k; int B, N, L, EPB; crowdsim_state st; double *next_pos, *next_vel; };
+
+__global__ void __launch_bounds__(256) lookahead_humans_kernel(const __grid_constant__ NextArgs G)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int T = blockDim.x, tid = threadIdx.x;
+    const int N = G.N, L = G.L;
+    const KParams &k = G.k;
+    const Stage s = carve_stage(smem, G.EPB, L, k.nb_alloc, T);
+    const int le = tid / L, a = tid - le * L;
+    const int e = blockIdx.x * G.EPB + le;
+    const bool is_robot = (a == N);
+    const bool live = (e < G.B);
+    double2 pos = make_double2(0, 0), vel = pos, goal = pos, attr = pos;
+    if (live) {
+        if (!is_robot) { const size_t i = (size_t)e * N + a; pos = ld2(G.st.h_pos, i); vel = ld2(G.st.h_vel, i); goal = ld2(G.st.h_goal, i); attr = ld2(G.st.h_attr, i); }
+        else { pos = ld2(G.st.r_pos, e); vel = ld2(G.st.r_vel, e); attr = ld2(G.st.r_attr, e); }
+    }
+    stage_agent(s, k, tid, pos, vel, attr.x);
+    __syncthreads();
+    if (live && !is_robot) {
+        const orca::V2 nv = orca_predict(s, k, le, a, N, L, pos, goal, attr.y, tid, T);
+        const double hx = (double)nv.x, hy = (double)nv.y;
+        const size_t i = (size_t)e * N + a;
+        st2(G.next_pos, i, make_double2(pos.x + hx * k.time_step, pos.y + hy * k.time_step));
+        st2(G.next_vel, i, make_double2(hx, hy));
+    }
+}
+
+// ---- MultiHumanRL.build_occupancy_maps (crowd_nav/policy/multi_human_rl.py:109-163): for every human i a cell_num x
+// cell_num grid (cell_size metres per cell) centred on i and aligned with i's velocity; channels = 1: occupancy,
+// 2: mean (vx, vy) of the occupants in i's frame, 3: (occupied, mean vx, mean vy). One thread per (env, human);
+// float64 like the reference's numpy code, output float32 like its torch tensor. ----
+#define CS_OM_MAX_CELLS 64
+struct OmArgs { int B, N, cell_num, channels; double cell_size; const double *pos, *vel; float *out; };
+
+__global__ void __launch_bounds__(128) occupancy_kernel(const __grid_constant__ OmArgs G)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)G.B * G.N) return;
+    const int N = G.N, e = (int)(idx / N), i = (int)(idx - (size_t)e * N);
+    const int cells = G.cell_num * G.cell_num, C = G.channels;
+    double sx[CS_OM_MAX_CELLS], sy[CS_OM_MAX_CELLS]; int cnt[CS_OM_MAX_CELLS];
+    for (int c = 0; c < cells; ++c) { sx[c] = 0.0; sy[c] = 0.0; cnt[c] = 0; }
+    const double2 pi = ld2(G.pos, idx), vi = ld2(G.vel, idx);
+    const double angle = atan2(vi.y, vi.x);                                  // :124 new x-axis along the human's velocity
+    const double half = (double)G.cell_num / 2;
+    for (int j = 0; j < N; ++j) {
+        if (j == i) continue;
+        const double2 pj = ld2(G.pos, (size_t)e * N + j), vj = ld2(G.vel, (size_t)e * N + j);
+        const double ox = pj.x - pi.x, oy = pj.y - pi.y;
+        const double rot = atan2(oy, ox) - angle;
+        const double dist = sqrt(ox * ox + oy * oy);                         // :127 np.linalg.norm(axis=0)
+        const double rx = cos(rot) * dist, ry = sin(rot) * dist;
+        const double xi = floor(rx / G.cell_size + half), yi = floor(ry / G.cell_size + half);
+        if (!(xi >= 0 && xi < G.cell_num && yi >= 0 && yi < G.cell_num)) continue;     // :134-137 (-inf = outside)
+        const int cell = G.cell_num * (int)yi + (int)xi;
+        const double vrot = atan2(vj.y, vj.x) - angle;                      // :144-148
+        const double speed = sqrt(vj.x * vj.x + vj.y * vj.y);
+        sx[cell] += cos(vrot) * speed; sy[cell] += sin(vrot) * speed; cnt[cell] += 1;
+    }
+    float *o = G.out + idx * (size_t)(cells * C);
+    for (int c = 0; c < cells; ++c) {
+        const bool occ = cnt[c] > 0;
+        const double mx = occ ? sx[c] / cnt[c] : 0.0, my = occ ? sy[c] / cnt[c] : 0.0;
+        if (C == 1) o[c] = occ ? 1.f : 0.f;
+        else if (C == 2) { o[2 * c] = (float)mx; o[2 * c + 1] = (float)my; }
+        else { o[3 * c] = occ ? 1.f : 0.f; o[3 * c + 1] = (float)mx; o[3 * c + 2] = (float)my; }
+    }
+}
+
 }  // namespace cs
 
 extern "C" int crowdsim_pack_joint(int B, int N, const crowdsim_state *st, int kinematics_unicycle, float *out, void *stream)
@@ -207,6 +281,42 @@ extern "C" int crowdsim_lookahead_pack(const crowdsim_params *prm, int B, int N,
         if (err != cudaSuccess) return (int)err;
     }
     cs::lookahead_kernel<<<blocks, threads, smem, (cudaStream_t)stream>>>(G);
+    ++cs::g_launches;
+    return (int)cudaGetLastError();
+}
+
+extern "C" int crowdsim_lookahead_humans(const crowdsim_params *prm, int B, int N, const crowdsim_state *st,
+                                         double *next_h_pos, double *next_h_vel, void *stream)
+{
+    if (!prm || !st || !next_h_pos || !next_h_vel || B < 0 || N < 1) return CROWDSIM_EINVAL;
+    if (N > CROWDSIM_MAX_HUMANS || prm->max_neighbors > CROWDSIM_MAX_NEIGHBORS) return CROWDSIM_EUNSUPPORTED;
+    if (!st->h_pos || !st->h_vel || !st->h_goal || !st->h_attr || !st->r_pos || !st->r_vel || !st->r_attr) return CROWDSIM_EINVAL;
+    if (B == 0) return CROWDSIM_OK;
+    cs::NextArgs G;
+    G.k = cs::make_kparams(prm, N);
+    G.B = B; G.N = N; G.L = N + 1; G.EPB = cs::envs_per_block(G.L, 128); G.st = *st; G.next_pos = next_h_pos; G.next_vel = next_h_vel;
+    const int threads = G.EPB * G.L;
+    const int blocks = (B + G.EPB - 1) / G.EPB;
+    const size_t smem = cs::stage_bytes(G.EPB, G.L, G.k.nb_alloc, threads);
+    if (smem > 227 * 1024) return CROWDSIM_EUNSUPPORTED;
+    if (smem > 48 * 1024) {
+        cudaError_t err = cudaFuncSetAttribute(cs::lookahead_humans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return (int)err;
+    }
+    cs::lookahead_humans_kernel<<<blocks, threads, smem, (cudaStream_t)stream>>>(G);
+    ++cs::g_launches;
+    return (int)cudaGetLastError();
+}
+
+extern "C" int crowdsim_occupancy_maps(int B, int N, const double *h_pos, const double *h_vel, int cell_num, double cell_size,
+                                       int channels, float *out, void *stream)
+{
+    if (!h_pos || !h_vel || !out || B < 0 || N < 2 || cell_num < 1 || !(cell_size > 0) || channels < 1 || channels > 3) return CROWDSIM_EINVAL;
+    if (cell_num * cell_num > CS_OM_MAX_CELLS) return CROWDSIM_EUNSUPPORTED;
+    if (B == 0) return CROWDSIM_OK;
+    cs::OmArgs G; G.B = B; G.N = N; G.cell_num = cell_num; G.channels = channels; G.cell_size = cell_size; G.pos = h_pos; G.vel = h_vel; G.out = out;
+    const size_t n = (size_t)B * N; const int threads = 128; const int blocks = (int)((n + threads - 1) / threads);
+    cs::occupancy_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(G);
     ++cs::g_launches;
     return (int)cudaGetLastError();
 }

@@ -45,63 +45,112 @@ struct MT {
     }
 };
 
-// Scene of one env: N humans by rejection sampling (crowd_sim.py:155-207), written to hp/hg/ha ([N][2] each).
+// Scene of one env: N humans by rejection sampling (crowd_sim.py:84-207), written to hp/hg/ha ([N][2] each).
 // The robot is fixed at (0, -R) -> (0, R) (crowd_sim.py:274) and takes part in the separation tests.
+// Rule `mixed` (crowd_sim.py:103-151) draws the number of humans per scene (0..5, capped at N); the remaining slots of
+// the fixed-N layout are PARKED: position = goal = (CROWDSIM_PARKED_X + 100 i, CROWDSIM_PARKED_X), i.e. outside every
+// neighbour range and far from the robot, so they take no part in any solve, collision test or minimum distance.
 __device__ __forceinline__ void generate_scene(MT &rng, const crowdsim_reset_args &a, int N, double *hp, double *hg, double *ha)
 {
     const double rpx = 0.0, rpy = -a.circle_radius, rgx = 0.0, rgy = a.circle_radius;
-    for (int i = 0; i < N; ++i) {
-        double radius = a.human_radius, v_pref = a.human_v_pref;
+    auto put = [&](int i, double px, double py, double gx, double gy, double radius, double v_pref) {
+        hp[2 * i] = px; hp[2 * i + 1] = py; hg[2 * i] = gx; hg[2 * i + 1] = gy; ha[2 * i] = radius; ha[2 * i + 1] = v_pref;
+    };
+    auto attributes = [&](double &radius, double &v_pref) {
+        radius = a.human_radius; v_pref = a.human_v_pref;
         if (a.randomize_attributes) {                      // agent.py:44-45
             v_pref = 0.5 + (1.5 - 0.5) * rng.next_double();
             radius = 0.3 + (0.5 - 0.3) * rng.next_double();
         }
-        double px, py, gx, gy;
-        if (a.rule == CROWDSIM_RULE_CIRCLE) {              // crowd_sim.py:155-176
-            for (;;) {
-                const double angle = rng.next_double() * CS_PI * 2;
-                const double px_noise = (rng.next_double() - 0.5) * v_pref;
-                const double py_noise = (rng.next_double() - 0.5) * v_pref;
-                px = a.circle_radius * cos(angle) + px_noise;
-                py = a.circle_radius * sin(angle) + py_noise;
-                bool collide = false;
-                for (int k = -1; k < i && !collide; ++k) {
-                    const double ar = (k < 0) ? a.robot_radius : ha[2 * k];
-                    const double apx = (k < 0) ? rpx : hp[2 * k], apy = (k < 0) ? rpy : hp[2 * k + 1];
-                    const double agx = (k < 0) ? rgx : hg[2 * k], agy = (k < 0) ? rgy : hg[2 * k + 1];
-                    const double min_dist = radius + ar + a.discomfort_dist;
-                    if (norm2(px - apx, py - apy) < min_dist || norm2(px - agx, py - agy) < min_dist) collide = true;
-                }
-                if (!collide) break;
+    };
+    auto circle_human = [&](int i) {                       // crowd_sim.py:155-176
+        double radius, v_pref, px, py; attributes(radius, v_pref);
+        for (;;) {
+            const double angle = rng.next_double() * CS_PI * 2;
+            const double px_noise = (rng.next_double() - 0.5) * v_pref;
+            const double py_noise = (rng.next_double() - 0.5) * v_pref;
+            px = a.circle_radius * cos(angle) + px_noise;
+            py = a.circle_radius * sin(angle) + py_noise;
+            bool collide = false;
+            for (int k = -1; k < i && !collide; ++k) {
+                const double ar = (k < 0) ? a.robot_radius : ha[2 * k];
+                const double apx = (k < 0) ? rpx : hp[2 * k], apy = (k < 0) ? rpy : hp[2 * k + 1];
+                const double agx = (k < 0) ? rgx : hg[2 * k], agy = (k < 0) ? rgy : hg[2 * k + 1];
+                const double min_dist = radius + ar + a.discomfort_dist;
+                if (norm2(px - apx, py - apy) < min_dist || norm2(px - agx, py - agy) < min_dist) collide = true;
             }
-            gx = -px; gy = -py;
-        } else {                                           // crowd_sim.py:178-207
-            const double sign = (rng.next_double() > 0.5) ? -1.0 : 1.0;
-            for (;;) {
-                px = rng.next_double() * a.square_width * 0.5 * sign;
-                py = (rng.next_double() - 0.5) * a.square_width;
-                bool collide = false;
-                for (int k = -1; k < i && !collide; ++k) {
-                    const double ar = (k < 0) ? a.robot_radius : ha[2 * k];
-                    const double apx = (k < 0) ? rpx : hp[2 * k], apy = (k < 0) ? rpy : hp[2 * k + 1];
-                    if (norm2(px - apx, py - apy) < radius + ar + a.discomfort_dist) collide = true;
-                }
-                if (!collide) break;
-            }
-            for (;;) {
-                gx = rng.next_double() * a.square_width * 0.5 * -sign;
-                gy = (rng.next_double() - 0.5) * a.square_width;
-                bool collide = false;
-                for (int k = -1; k < i && !collide; ++k) {
-                    const double ar = (k < 0) ? a.robot_radius : ha[2 * k];
-                    const double agx = (k < 0) ? rgx : hg[2 * k], agy = (k < 0) ? rgy : hg[2 * k + 1];
-                    if (norm2(gx - agx, gy - agy) < radius + ar + a.discomfort_dist) collide = true;
-                }
-                if (!collide) break;
-            }
+            if (!collide) break;
         }
-        hp[2 * i] = px; hp[2 * i + 1] = py; hg[2 * i] = gx; hg[2 * i + 1] = gy;
-        ha[2 * i] = radius; ha[2 * i + 1] = v_pref;
+        put(i, px, py, -px, -py, radius, v_pref);
+    };
+    auto square_human = [&](int i) {                       // crowd_sim.py:178-207
+        double radius, v_pref, px, py, gx, gy; attributes(radius, v_pref);
+        const double sign = (rng.next_double() > 0.5) ? -1.0 : 1.0;
+        for (;;) {
+            px = rng.next_double() * a.square_width * 0.5 * sign;
+            py = (rng.next_double() - 0.5) * a.square_width;
+            bool collide = false;
+            for (int k = -1; k < i && !collide; ++k) {
+                const double ar = (k < 0) ? a.robot_radius : ha[2 * k];
+                const double apx = (k < 0) ? rpx : hp[2 * k], apy = (k < 0) ? rpy : hp[2 * k + 1];
+                if (norm2(px - apx, py - apy) < radius + ar + a.discomfort_dist) collide = true;
+            }
+            if (!collide) break;
+        }
+        for (;;) {
+            gx = rng.next_double() * a.square_width * 0.5 * -sign;
+            gy = (rng.next_double() - 0.5) * a.square_width;
+            bool collide = false;
+            for (int k = -1; k < i && !collide; ++k) {
+                const double ar = (k < 0) ? a.robot_radius : ha[2 * k];
+                const double agx = (k < 0) ? rgx : hg[2 * k], agy = (k < 0) ? rgy : hg[2 * k + 1];
+                if (norm2(gx - agx, gy - agy) < radius + ar + a.discomfort_dist) collide = true;
+            }
+            if (!collide) break;
+        }
+        put(i, px, py, gx, gy, radius, v_pref);
+    };
+    if (a.rule == CROWDSIM_RULE_CIRCLE) { for (int i = 0; i < N; ++i) circle_human(i); return; }
+    if (a.rule == CROWDSIM_RULE_SQUARE) { for (int i = 0; i < N; ++i) square_human(i); return; }
+    // ---- mixed (crowd_sim.py:103-151) ----
+    const bool is_static = rng.next_double() < 0.2;
+    double prob = rng.next_double();
+    const double p_static[6] = {0.05, 0.2, 0.2, 0.3, 0.1, 0.15}, p_dynamic[6] = {0.0, 0.3, 0.3, 0.2, 0.1, 0.1};
+    int count = N;                                         // the reference keeps its previous human_num if no key matches
+    for (int key = is_static ? 0 : 1; key <= 5; ++key) {
+        const double value = is_static ? p_static[key] : p_dynamic[key];
+        if (prob - value <= 0) { count = key; break; }
+        prob -= value;
+    }
+    if (count > N) count = N;
+    int placed = 0;
+    if (is_static) {                                       // standing humans in a 4 x 8 box, goal = position
+        const double width = 4, height = 8;
+        if (count == 0 && N > 0) { put(0, 0.0, -10.0, 0.0, -10.0, a.human_radius, a.human_v_pref); placed = 1; }   // :121-124 dummy
+        for (int i = 0; i < count; ++i) {
+            const double sign = (rng.next_double() > 0.5) ? -1.0 : 1.0;
+            double px, py;
+            for (;;) {
+                px = rng.next_double() * width * 0.5 * sign;
+                py = (rng.next_double() - 0.5) * height;
+                bool collide = false;
+                for (int k = -1; k < i && !collide; ++k) {
+                    const double ar = (k < 0) ? a.robot_radius : ha[2 * k];
+                    const double apx = (k < 0) ? rpx : hp[2 * k], apy = (k < 0) ? rpy : hp[2 * k + 1];
+                    if (norm2(px - apx, py - apy) < a.human_radius + ar + a.discomfort_dist) collide = true;
+                }
+                if (!collide) break;
+            }
+            put(i, px, py, px, py, a.human_radius, a.human_v_pref);
+        }
+        if (count > 0) placed = count;
+    } else {                                               // two circle-crossing humans, the rest square-crossing
+        for (int i = 0; i < count; ++i) { if (i < 2) circle_human(i); else square_human(i); }
+        placed = count;
+    }
+    for (int i = placed; i < N; ++i) {
+        const double x = CROWDSIM_PARKED_X + 100.0 * i;
+        put(i, x, CROWDSIM_PARKED_X, x, CROWDSIM_PARKED_X, a.human_radius, a.human_v_pref);
     }
 }
 
@@ -226,7 +275,8 @@ static int check_reset_args(const crowdsim_reset_args *args, int B, int N)
     if (!args || B < 0 || N < 0) return CROWDSIM_EINVAL;
     if (!args->case_counter && !args->seed) return CROWDSIM_EINVAL;
     if (N > CROWDSIM_MAX_HUMANS) return CROWDSIM_EUNSUPPORTED;
-    if (args->rule != CROWDSIM_RULE_CIRCLE && args->rule != CROWDSIM_RULE_SQUARE) return CROWDSIM_EUNSUPPORTED;
+    if (args->rule != CROWDSIM_RULE_CIRCLE && args->rule != CROWDSIM_RULE_SQUARE && args->rule != CROWDSIM_RULE_MIXED) return CROWDSIM_EUNSUPPORTED;
+    if (args->rule == CROWDSIM_RULE_MIXED && N < 5) return CROWDSIM_EUNSUPPORTED;      // the rule draws up to 5 humans whatever N is
     return CROWDSIM_OK;
 }
 

@@ -145,7 +145,8 @@ class BatchedExplorer(object):
         recorder = None
         if update_memory:
             from .memory import TrajectoryRecorder
-            recorder = TrajectoryRecorder(env, self.memory, self.gamma, imitation_learning, self.target_model)
+            om = getattr(self.robot_policy, 'om', None) if getattr(self.robot_policy, 'with_om', False) else None
+            recorder = TrajectoryRecorder(env, self.memory, self.gamma, imitation_learning, self.target_model, om=om)
         side = torch.cuda.Stream(device=env.device)
         main = torch.cuda.current_stream(env.device)
         it = 0

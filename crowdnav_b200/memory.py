@@ -52,12 +52,16 @@ class DeviceReplayMemory(object):
 
 
 class TrajectoryRecorder(object):
-    def __init__(self, env, memory, gamma, imitation_learning=True, target_model=None, max_steps=128):
+    def __init__(self, env, memory, gamma, imitation_learning=True, target_model=None, max_steps=128, om=None):
+        """om = None or (cell_num, cell_size, om_channel_size): append the occupancy maps of the current human states to
+        every recorded row, as MultiHumanRL.transform does with with_om (multi_human_rl.py:98-104)."""
         self.env, self.memory = env, memory
+        self.om = om
+        F = 13 + (om[0] * om[0] * om[2] if om else 0)
         self.il, self.target_model = imitation_learning, target_model
         B, N, dev = env.B, env.human_num, env.device
         self.T = max_steps
-        self.states = torch.zeros((B, self.T, N, 13), dtype=torch.float32, device=dev)
+        self.states = torch.zeros((B, self.T, N, F), dtype=torch.float32, device=dev)
         self.rewards = torch.zeros((B, self.T), dtype=torch.float64, device=dev)
         self.returns = torch.zeros((B, self.T), dtype=torch.float64, device=dev)
         expo = env.time_step * env.robot_v_pref
@@ -74,6 +78,8 @@ class TrajectoryRecorder(object):
         self._t = env.episodes.ep_steps.long().clamp_(max=self.T - 1)
         self._live = env.state.active.bool()
         packed = env.pack_joint()
+        if self.om:
+            packed = torch.cat([packed, env.occupancy_maps(None, None, *self.om)], dim=2)
         rows = torch.arange(env.B, device=env.device)
         self.states[rows, self._t] = torch.where(self._live.view(-1, 1, 1), packed, self.states[rows, self._t])
 

@@ -130,8 +130,13 @@ class BatchedValuePolicy(object):
     trainable = True
     multiagent_training = True
 
-    def __init__(self, model, gamma=0.9, v_pref=1.0, time_step=0.25, joint=True, speed_samples=5, rotation_samples=16):
+    def __init__(self, model, gamma=0.9, v_pref=1.0, time_step=0.25, joint=True, speed_samples=5, rotation_samples=16,
+                 with_om=False, cell_num=4, cell_size=1.0, om_channel_size=3):
         self.model = model
+        # policy.config [om] + with_om: occupancy maps of the NEXT human states are appended to every row
+        # (multi_human_rl.py:46-49; they do not depend on the action, so they are built once per env and broadcast)
+        self.with_om = with_om
+        self.om = (cell_num, cell_size, om_channel_size)
         self.gamma = gamma
         self.v_pref, self.time_step = v_pref, time_step
         self.joint = joint
@@ -164,8 +169,14 @@ class BatchedValuePolicy(object):
             self._buf_reward = torch.empty((B, A), dtype=torch.float64, device=self.device)
         states, reward = env.lookahead_pack(self.actions, out_states=self._buf_states, out_reward=self._buf_reward)
         discount = pow(self.gamma, self.time_step * self.v_pref)
+        F = 13
+        if self.with_om:
+            npos, nvel = env.lookahead_humans()
+            om = env.occupancy_maps(npos, nvel, *self.om)                # [B][N][cells * channels]
+            states = torch.cat([states, om.unsqueeze(1).expand(B, A, N, om.shape[2])], dim=3)
+            F = states.shape[3]
         if self.joint:
-            v = self.model(states.view(B * A, N, 13)).view(B, A)
+            v = self.model(states.reshape(B * A, N, F)).view(B, A)
         else:
             v = self.model(states.view(B * A * N, 13)).view(B, A, N).min(dim=2).values
         values = reward + discount * v.double()                        # python-float arithmetic in the reference
@@ -178,13 +189,18 @@ class BatchedValuePolicy(object):
         return torch.where(reached.unsqueeze(1), torch.zeros_like(act), act)
 
 
-def make_sarl(gamma=0.9, v_pref=1.0, time_step=0.25, seed=None, **net_kw):
+def make_sarl(gamma=0.9, v_pref=1.0, time_step=0.25, seed=None, with_om=False, cell_num=4, cell_size=1.0,
+              om_channel_size=3, **net_kw):
     """SARL with the reference's default architecture (crowd_nav/configs/policy.config:43-50); random-init weights when
-    no checkpoint is loaded (there are no checkpoints in the reference repo)."""
+    no checkpoint is loaded (there are no checkpoints in the reference repo). with_om=True gives OM-SARL: input_dim grows
+    by cell_num^2 * om_channel_size (multi_human_rl.py:106-107)."""
     if seed is not None:
         torch.manual_seed(seed)
-    p = BatchedValuePolicy(SARLValueNetwork(**net_kw), gamma, v_pref, time_step, joint=True)
-    p.name = 'SARL'
+    if with_om:
+        net_kw.setdefault('input_dim', 13 + cell_num * cell_num * om_channel_size)
+    p = BatchedValuePolicy(SARLValueNetwork(**net_kw), gamma, v_pref, time_step, joint=True, with_om=with_om,
+                           cell_num=cell_num, cell_size=cell_size, om_channel_size=om_channel_size)
+    p.name = 'OM-SARL' if with_om else 'SARL'
     return p
 
 

@@ -21,6 +21,8 @@
  *                            (crowd_sim.py:314-315,414-416) + CADRL.propagate (cadrl.py:104-129) +
  *                            CADRL.rotate (cadrl.py:187-222), fused
  *   crowdsim_pack_joint      crowd_sim/envs/utils/state.py:17-18,36-37 (14-tuple) + cadrl.py:187-222 (rotate)
+ *   crowdsim_lookahead_humans  the observation of env.onestep_lookahead (crowd_sim.py:314-315,414-416; agent.py:63-74)
+ *   crowdsim_occupancy_maps  crowd_nav/policy/multi_human_rl.py:109-163 (MultiHumanRL.build_occupancy_maps)
  *
  * Layout in HBM (structure of arrays, float64 like the reference's Python floats):
  *   two-vectors are interleaved (x,y) pairs so one agent's pair is one 16-byte load;
@@ -61,6 +63,12 @@ extern "C" {
 /* scenario rules: crowd_sim.py:84-153 */
 #define CROWDSIM_RULE_CIRCLE 0
 #define CROWDSIM_RULE_SQUARE 1
+/* crowd_sim.py:103-151: per scene 0..5 humans, standing (20 %) or two circle- + the rest square-crossing. The arrays keep
+ * their fixed N; unused human slots are PARKED at position = goal = (CROWDSIM_PARKED_X + 100 i, CROWDSIM_PARKED_X): out of
+ * every neighbour range (neighbor_dist must stay below 100) and of every collision / min-distance test, never moving.
+ * A consumer counts the present humans of env e as #{i : h_pos[e][i].x < CROWDSIM_PARKED_X / 2}. */
+#define CROWDSIM_RULE_MIXED 2
+#define CROWDSIM_PARKED_X 1.0e6
 
 typedef struct crowdsim_params {
     /* crowd_nav/configs/env.config [env] / [reward]; crowd_sim.py:51-60 */
@@ -226,6 +234,24 @@ int crowdsim_pack_joint(int B, int N, const crowdsim_state *st, int kinematics_u
 int crowdsim_lookahead_pack(const crowdsim_params *prm, int B, int N, const crowdsim_state *st,
                             const double *actions, int A, int kinematics_unicycle,
                             float *out_states, double *out_reward, void *stream);
+
+/*
+ * The humans' next observable states for the current state and the humans' own ORCA decisions -- what
+ * env.onestep_lookahead(action) returns as `ob` (it does not depend on the robot's action): next_h_pos, next_h_vel
+ * [B][N][2] float64. Nothing is mutated.
+ */
+int crowdsim_lookahead_humans(const crowdsim_params *prm, int B, int N, const crowdsim_state *st,
+                              double *next_h_pos, double *next_h_vel, void *stream);
+
+/*
+ * Occupancy maps of MultiHumanRL.build_occupancy_maps (multi_human_rl.py:109-163; policy.config [om] cell_num,
+ * cell_size, om_channel_size) for B x N humans given as [B][N][2] float64 position / velocity arrays (the live state or
+ * the output of crowdsim_lookahead_humans): out [B][N][cell_num^2 * channels] float32, cell-major, channels 1 (occupied),
+ * 2 (mean vx, vy of the occupants in the human's velocity-aligned frame) or 3 (occupied, mean vx, mean vy).
+ * N >= 2 (the reference raises for a single human); cell_num^2 <= 64.
+ */
+int crowdsim_occupancy_maps(int B, int N, const double *h_pos, const double *h_vel, int cell_num, double cell_size,
+                            int channels, float *out, void *stream);
 
 #ifdef __cplusplus
 }

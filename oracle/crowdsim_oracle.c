@@ -102,63 +102,125 @@ static int next_seed(const crowdsim_reset_args *a, int e, uint32_t *seed, int *c
     return 1;
 }
 
-/* N humans by rejection sampling into hp/hg/ha ([N][2] each); crowd_sim.py:155-207, agent.py:39-45 */
+/* One circle-crossing human i (crowd_sim.py:155-176, agent.py:39-45) appended to hp/hg/ha. */
+static void gen_circle_human(mt_state *rng, const crowdsim_reset_args *a, int i, double *hp, double *hg, double *ha)
+{
+    const double rpx = 0.0, rpy = -a->circle_radius, rgx = 0.0, rgy = a->circle_radius;
+    double radius = a->human_radius, v_pref = a->human_v_pref, px, py;
+    if (a->randomize_attributes) {            /* agent.py:44-45: v_pref first, then radius */
+        v_pref = 0.5 + (1.5 - 0.5) * mt_double(rng);
+        radius = 0.3 + (0.5 - 0.3) * mt_double(rng);
+    }
+    for (;;) {
+        const double angle = mt_double(rng) * PI_D * 2;
+        const double px_noise = (mt_double(rng) - 0.5) * v_pref;
+        const double py_noise = (mt_double(rng) - 0.5) * v_pref;
+        px = a->circle_radius * cos(angle) + px_noise;
+        py = a->circle_radius * sin(angle) + py_noise;
+        int collide = 0;
+        for (int k = -1; k < i && !collide; ++k) {   /* [robot] + humans so far */
+            const double ar = (k < 0) ? a->robot_radius : ha[2 * k];
+            const double apx = (k < 0) ? rpx : hp[2 * k], apy = (k < 0) ? rpy : hp[2 * k + 1];
+            const double agx = (k < 0) ? rgx : hg[2 * k], agy = (k < 0) ? rgy : hg[2 * k + 1];
+            const double min_dist = radius + ar + a->discomfort_dist;
+            if (norm2(px - apx, py - apy) < min_dist || norm2(px - agx, py - agy) < min_dist) collide = 1;
+        }
+        if (!collide) break;
+    }
+    hp[2 * i] = px; hp[2 * i + 1] = py; hg[2 * i] = -px; hg[2 * i + 1] = -py; ha[2 * i] = radius; ha[2 * i + 1] = v_pref;
+}
+
+/* One square-crossing human i (crowd_sim.py:178-207). */
+static void gen_square_human(mt_state *rng, const crowdsim_reset_args *a, int i, double *hp, double *hg, double *ha)
+{
+    const double rpx = 0.0, rpy = -a->circle_radius, rgx = 0.0, rgy = a->circle_radius;
+    double radius = a->human_radius, v_pref = a->human_v_pref, px, py, gx, gy;
+    if (a->randomize_attributes) {
+        v_pref = 0.5 + (1.5 - 0.5) * mt_double(rng);
+        radius = 0.3 + (0.5 - 0.3) * mt_double(rng);
+    }
+    const double sign = (mt_double(rng) > 0.5) ? -1.0 : 1.0;
+    for (;;) {
+        px = mt_double(rng) * a->square_width * 0.5 * sign;
+        py = (mt_double(rng) - 0.5) * a->square_width;
+        int collide = 0;
+        for (int k = -1; k < i && !collide; ++k) {
+            const double ar = (k < 0) ? a->robot_radius : ha[2 * k];
+            const double apx = (k < 0) ? rpx : hp[2 * k], apy = (k < 0) ? rpy : hp[2 * k + 1];
+            if (norm2(px - apx, py - apy) < radius + ar + a->discomfort_dist) collide = 1;
+        }
+        if (!collide) break;
+    }
+    for (;;) {
+        gx = mt_double(rng) * a->square_width * 0.5 * -sign;
+        gy = (mt_double(rng) - 0.5) * a->square_width;
+        int collide = 0;
+        for (int k = -1; k < i && !collide; ++k) {
+            const double ar = (k < 0) ? a->robot_radius : ha[2 * k];
+            const double agx = (k < 0) ? rgx : hg[2 * k], agy = (k < 0) ? rgy : hg[2 * k + 1];
+            if (norm2(gx - agx, gy - agy) < radius + ar + a->discomfort_dist) collide = 1;
+        }
+        if (!collide) break;
+    }
+    hp[2 * i] = px; hp[2 * i + 1] = py; hg[2 * i] = gx; hg[2 * i + 1] = gy; ha[2 * i] = radius; ha[2 * i + 1] = v_pref;
+}
+
+/* N human slots of one scene into hp/hg/ha ([N][2] each): crowd_sim.py:84-153 (rule dispatch incl. `mixed`), :155-207. */
 static void generate_scene(mt_state *rngp, const crowdsim_reset_args *a, int N, double *hp, double *hg, double *ha)
 {
     mt_state rng = *rngp;
-    const double rpx = 0.0, rpy = -a->circle_radius, rgx = 0.0, rgy = a->circle_radius;
-    for (int i = 0; i < N; ++i) {
-        double radius = a->human_radius, v_pref = a->human_v_pref;
-        if (a->randomize_attributes) {            /* agent.py:44-45: v_pref first, then radius */
-            v_pref = 0.5 + (1.5 - 0.5) * mt_double(&rng);
-            radius = 0.3 + (0.5 - 0.3) * mt_double(&rng);
+    if (a->rule == CROWDSIM_RULE_CIRCLE) {
+        for (int i = 0; i < N; ++i) gen_circle_human(&rng, a, i, hp, hg, ha);
+    } else if (a->rule == CROWDSIM_RULE_SQUARE) {
+        for (int i = 0; i < N; ++i) gen_square_human(&rng, a, i, hp, hg, ha);
+    } else {
+        /* mixed, crowd_sim.py:103-151. static_human_num = {0: .05, 1: .2, 2: .2, 3: .3, 4: .1, 5: .15} with probability 0.2,
+         * else dynamic_human_num = {1: .3, 2: .3, 3: .2, 4: .1, 5: .1}; keys visited in ascending order (:109). */
+        static const double p_static[6] = {0.05, 0.2, 0.2, 0.3, 0.1, 0.15}, p_dynamic[6] = {0.0, 0.3, 0.3, 0.2, 0.1, 0.1};
+        const int is_static = mt_double(&rng) < 0.2;
+        double prob = mt_double(&rng);
+        int count = N, placed = 0;
+        for (int key = is_static ? 0 : 1; key <= 5; ++key) {
+            const double value = is_static ? p_static[key] : p_dynamic[key];
+            if (prob - value <= 0) { count = key; break; }
+            prob -= value;
         }
-        double px, py, gx, gy;
-        if (a->rule == CROWDSIM_RULE_CIRCLE) {     /* crowd_sim.py:155-176 */
-            for (;;) {
-                const double angle = mt_double(&rng) * PI_D * 2;
-                const double px_noise = (mt_double(&rng) - 0.5) * v_pref;
-                const double py_noise = (mt_double(&rng) - 0.5) * v_pref;
-                px = a->circle_radius * cos(angle) + px_noise;
-                py = a->circle_radius * sin(angle) + py_noise;
-                int collide = 0;
-                for (int k = -1; k < i && !collide; ++k) {   /* [robot] + humans so far */
-                    const double ar = (k < 0) ? a->robot_radius : ha[2 * k];
-                    const double apx = (k < 0) ? rpx : hp[2 * k], apy = (k < 0) ? rpy : hp[2 * k + 1];
-                    const double agx = (k < 0) ? rgx : hg[2 * k], agy = (k < 0) ? rgy : hg[2 * k + 1];
-                    const double min_dist = radius + ar + a->discomfort_dist;
-                    if (norm2(px - apx, py - apy) < min_dist || norm2(px - agx, py - agy) < min_dist) collide = 1;
-                }
-                if (!collide) break;
+        if (count > N) count = N;
+        if (is_static) {
+            const double width = 4, height = 8;            /* :119-120 */
+            if (count == 0 && N > 0) {                     /* :121-124 a dummy human far below the scene */
+                hp[0] = 0.0; hp[1] = -10.0; hg[0] = 0.0; hg[1] = -10.0; ha[0] = a->human_radius; ha[1] = a->human_v_pref;
+                placed = 1;
             }
-            gx = -px; gy = -py;
-        } else {                                   /* crowd_sim.py:178-207 */
-            const double sign = (mt_double(&rng) > 0.5) ? -1.0 : 1.0;
-            for (;;) {
-                px = mt_double(&rng) * a->square_width * 0.5 * sign;
-                py = (mt_double(&rng) - 0.5) * a->square_width;
-                int collide = 0;
-                for (int k = -1; k < i && !collide; ++k) {
-                    const double ar = (k < 0) ? a->robot_radius : ha[2 * k];
-                    const double apx = (k < 0) ? rpx : hp[2 * k], apy = (k < 0) ? rpy : hp[2 * k + 1];
-                    if (norm2(px - apx, py - apy) < radius + ar + a->discomfort_dist) collide = 1;
+            for (int i = 0; i < count; ++i) {              /* :125-142 */
+                const double sign = (mt_double(&rng) > 0.5) ? -1.0 : 1.0;
+                double px, py;
+                for (;;) {
+                    px = mt_double(&rng) * width * 0.5 * sign;
+                    py = (mt_double(&rng) - 0.5) * height;
+                    int collide = 0;
+                    for (int k = -1; k < i && !collide; ++k) {
+                        const double ar = (k < 0) ? a->robot_radius : ha[2 * k];
+                        const double apx = (k < 0) ? 0.0 : hp[2 * k], apy = (k < 0) ? -a->circle_radius : hp[2 * k + 1];
+                        if (norm2(px - apx, py - apy) < a->human_radius + ar + a->discomfort_dist) collide = 1;
+                    }
+                    if (!collide) break;
                 }
-                if (!collide) break;
+                hp[2 * i] = px; hp[2 * i + 1] = py; hg[2 * i] = px; hg[2 * i + 1] = py;
+                ha[2 * i] = a->human_radius; ha[2 * i + 1] = a->human_v_pref;
             }
-            for (;;) {
-                gx = mt_double(&rng) * a->square_width * 0.5 * -sign;
-                gy = (mt_double(&rng) - 0.5) * a->square_width;
-                int collide = 0;
-                for (int k = -1; k < i && !collide; ++k) {
-                    const double ar = (k < 0) ? a->robot_radius : ha[2 * k];
-                    const double agx = (k < 0) ? rgx : hg[2 * k], agy = (k < 0) ? rgy : hg[2 * k + 1];
-                    if (norm2(gx - agx, gy - agy) < radius + ar + a->discomfort_dist) collide = 1;
-                }
-                if (!collide) break;
+            if (count > 0) placed = count;
+        } else {                                           /* :143-151 */
+            for (int i = 0; i < count; ++i) {
+                if (i < 2) gen_circle_human(&rng, a, i, hp, hg, ha); else gen_square_human(&rng, a, i, hp, hg, ha);
             }
+            placed = count;
         }
-        hp[2 * i] = px; hp[2 * i + 1] = py; hg[2 * i] = gx; hg[2 * i + 1] = gy;
-        ha[2 * i] = radius; ha[2 * i + 1] = v_pref;
+        for (int i = placed; i < N; ++i) {                 /* unused slots of the fixed-N layout: parked (crowdsim_b200.h) */
+            const double x = CROWDSIM_PARKED_X + 100.0 * i;
+            hp[2 * i] = x; hp[2 * i + 1] = CROWDSIM_PARKED_X; hg[2 * i] = x; hg[2 * i + 1] = CROWDSIM_PARKED_X;
+            ha[2 * i] = a->human_radius; ha[2 * i + 1] = a->human_v_pref;
+        }
     }
     *rngp = rng;
 }

@@ -13,6 +13,7 @@ What is recorded (floats as repr() strings, exact round trip):
   traj_*.json    full per-step trajectories of a few cases (every agent position/velocity, reward, info)
   reset_*.json   initial scenes straight after env.reset (scenario generators + MT19937)
   rotate.json    CADRL.rotate + one-step lookahead inputs/outputs of MultiHumanRL.predict's inner loop
+  occupancy_maps.json  MultiHumanRL.build_occupancy_maps on scene / lookahead / random human states
 
 usage: python oracle/gen_golden.py [--quick]
 """
@@ -89,10 +90,14 @@ def scene(env):
     }
 
 
-def run_suite(name, cases, phase='test', gamma=0.9, record_traj=(), fresh_robot_sim=False, **kw):
+def run_suite(name, cases, phase='test', gamma=0.9, record_traj=(), fresh_robot_sim=False, reset_human_num=None, **kw):
     """fresh_robot_sim: drop the robot's cached rvo2 sim before every episode. The reference keeps it across
     episodes (orca.py:95-104), so with randomize_attributes the robot would keep solving with the human radii of
     the FIRST episode it saw -- an accident of object lifetime we do not reproduce."""
+    """reset_human_num: rule `mixed` overwrites env.human_num with the drawn count (crowd_sim.py:115) and reset() sizes
+    human_times from the STALE value (:263), so the reference's own step() raises IndexError (:404-407) as soon as an
+    episode draws more humans than the previous one. The fixture driver therefore restores env.human_num before every
+    reset; the reference's Explorer cannot run such a suite at all (no log lines)."""
     env, robot, _ = make_env(**kw)
     # 1) the reference's own Explorer, capturing its log lines
     stream = io.StringIO()
@@ -103,7 +108,8 @@ def run_suite(name, cases, phase='test', gamma=0.9, record_traj=(), fresh_robot_
     root.setLevel(logging.INFO)
     explorer = Explorer(env, robot, torch.device('cpu'), gamma=gamma)
     env.case_counter[phase] = cases[0]
-    explorer.run_k_episodes(len(cases), phase, print_failure=True)
+    if reset_human_num is None:
+        explorer.run_k_episodes(len(cases), phase, print_failure=True)
     root.removeHandler(handler)
     log_lines = [l for l in stream.getvalue().splitlines() if l]
 
@@ -115,6 +121,8 @@ def run_suite(name, cases, phase='test', gamma=0.9, record_traj=(), fresh_robot_
     for case in cases:
         if fresh_robot_sim:
             robot.policy.sim = None
+        if reset_human_num is not None:
+            env.human_num = reset_human_num
         ob = env.reset(phase, case)
         init = scene(env)
         done = False
@@ -160,6 +168,10 @@ def run_suite(name, cases, phase='test', gamma=0.9, record_traj=(), fresh_robot_
     return out
 
 
+def run_mixed():
+    run_suite('mixed5_invisible', list(range(300)), human_num=5, test_sim='mixed', reset_human_num=5, record_traj=(1, 4, 8))
+
+
 def run_resets():
     """Initial scenes only: scenario generators + MT19937 (crowd_sim.py:155-207, 251-312)."""
     out = {}
@@ -170,6 +182,8 @@ def run_resets():
         ('circle10_test', dict(human_num=10, test_sim='circle_crossing'), 'test', list(range(0, 20))),
         ('circle5_random_attr', dict(human_num=5, test_sim='circle_crossing', randomize=True), 'test', list(range(0, 20))),
         ('square5_random_attr', dict(human_num=5, test_sim='square_crossing', randomize=True), 'test', list(range(0, 20))),
+        ('mixed5_test', dict(human_num=5, test_sim='mixed'), 'test', list(range(0, 120))),
+        ('mixed5_random_attr', dict(human_num=5, test_sim='mixed', randomize=True), 'test', list(range(0, 40))),
         ('circle5_train', dict(human_num=5, test_sim='circle_crossing'), 'train', [0, 1, 2, 1000, 123456, 4294965294]),
         ('circle5_val', dict(human_num=5, test_sim='circle_crossing'), 'val', [0, 1, 99]),
     ]:
@@ -232,7 +246,90 @@ def run_rotate():
     print('rotate/lookahead rows', len(rows))
 
 
+def run_om():
+    """MultiHumanRL.build_occupancy_maps (multi_human_rl.py:109-163), reference code only: (a) on the humans of real
+    scenes a few steps into test episodes and on the next human states env.onestep_lookahead returns, (b) on random
+    dense crowds (N = 3, 8, 20). Stored: inputs (px, py, vx, vy per human) and the reference's float32 maps."""
+    from crowd_sim.envs.utils.state import ObservableState
+    pcfg = configparser.RawConfigParser()
+    pcfg.read(os.path.join(REF, 'crowd_nav', 'configs', 'policy.config'))
+    torch.manual_seed(0)
+    env, robot, _ = make_env(human_num=5, test_sim='circle_crossing', policy_name='sarl', policy_config=pcfg)
+    policy = robot.policy
+    rows = []
+
+    def maps_for(states, tag, extra=None):
+        for cell_num, cell_size in ((4, 1.0), (6, 0.5), (8, 0.75)):
+            for ch in (1, 2, 3):
+                policy.cell_num, policy.cell_size, policy.om_channel_size = cell_num, cell_size, ch
+                om = policy.build_occupancy_maps(states)
+                row = {'tag': tag, 'cell_num': cell_num, 'cell_size': cell_size, 'channels': ch,
+                       'humans': [[R(h.px), R(h.py), R(h.vx), R(h.vy)] for h in states],
+                       'maps': [[R(v) for v in r] for r in om.reshape(len(states), -1).tolist()]}
+                if extra:
+                    row.update(extra)
+                rows.append(row)
+
+    for case in (0, 3):
+        ob = env.reset('test', case)
+        orca_robot = ORCA()
+        orca_robot.time_step = env.time_step
+        for step in range(13):
+            state = JointState(robot.get_full_state(), ob)
+            action = orca_robot.predict(state)
+            if step in (4, 12):
+                maps_for(ob, 'scene case %d step %d' % (case, step))
+                nxt, _, _, _ = env.onestep_lookahead(ActionXY(action.vx, action.vy))
+                maps_for(nxt, 'lookahead case %d step %d' % (case, step), {'scene': scene(env), 'global_time': R(env.global_time)})
+            ob, reward, done, info = env.step(ActionXY(action.vx, action.vy))
+            if done:
+                break
+    rng = np.random.RandomState(7)
+    for n in (3, 8, 20):
+        for rep in range(3):
+            states = [ObservableState(*rng.uniform(-2.5, 2.5, 2), *rng.uniform(-1, 1, 2), 0.3) for _ in range(n)]
+            if rep == 2:        # a standing human (atan2(0, 0) = 0) among them
+                states[0] = ObservableState(states[0].px, states[0].py, 0.0, 0.0, 0.3)
+            maps_for(states, 'random N=%d #%d' % (n, rep))
+    # OM-SARL decisions of the reference itself (policy.config [sarl] with_om = true, seed-0 weights): per-action values
+    # reward + gamma^(dt v_pref) * V(rotate(next state) ++ occupancy maps of the next human states) and the greedy action
+    pcfg.set('sarl', 'with_om', 'true')
+    torch.manual_seed(0)
+    env, robot, _ = make_env(human_num=5, test_sim='circle_crossing', policy_name='sarl', policy_config=pcfg)
+    policy = robot.policy
+    decisions = []
+    for case in (0, 3, 7):
+        ob = env.reset('test', case)
+        orca_robot = ORCA()
+        orca_robot.time_step = env.time_step
+        for step in range(12):
+            state = JointState(robot.get_full_state(), ob)
+            if step % 4 == 0:
+                np_state = np.random.get_state()
+                chosen = policy.predict(state)
+                np.random.set_state(np_state)
+                decisions.append({'case': case, 'step': step, 'scene': scene(env), 'global_time': R(env.global_time),
+                                  'action': [R(chosen.vx), R(chosen.vy)], 'values': [R(v) for v in policy.action_values]})
+            action = orca_robot.predict(state)
+            ob, reward, done, info = env.step(ActionXY(action.vx, action.vy))
+            if done:
+                break
+    with gzip.open(os.path.join(OUT, 'occupancy_maps.json.gz'), 'wt') as f:
+        json.dump({'rows': rows, 'om_sarl': {'seed': 0, 'gamma': policy.gamma, 'cell_num': policy.cell_num, 'cell_size': policy.cell_size,
+                                            'om_channel_size': policy.om_channel_size, 'decisions': decisions}}, f, separators=(',', ':'))
+    print('occupancy map rows', len(rows))
+
+
 def main():
+    if '--mixed-only' in sys.argv:
+        os.makedirs(OUT, exist_ok=True)
+        run_mixed()
+        run_resets()
+        return
+    if '--om-only' in sys.argv:
+        os.makedirs(OUT, exist_ok=True)
+        run_om()
+        return
     if '--rotate-only' in sys.argv:
         os.makedirs(OUT, exist_ok=True)
         run_rotate()
@@ -250,8 +347,10 @@ def main():
               robot_visible=True)
     run_suite('circle5_random_attr', list(range(20 if quick else 100)), human_num=5, test_sim='circle_crossing',
               randomize=True, fresh_robot_sim=True)
+    run_mixed()
     run_resets()
     run_rotate()
+    run_om()
 
 
 if __name__ == '__main__':

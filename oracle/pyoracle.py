@@ -79,6 +79,10 @@ class HostState(object):
         for i, h in enumerate(scene['humans']):
             h = [float(x) for x in h]
             self.h_pos[e, i] = h[0:2]; self.h_vel[e, i] = h[2:4]; self.h_goal[e, i] = h[4:6]; self.h_attr[e, i] = h[6:8]
+        for i in range(len(scene['humans']), self.N):      # `mixed` scenes with fewer humans: park the unused slots
+            x = _abi.PARKED_X + 100.0 * i
+            self.h_pos[e, i] = (x, _abi.PARKED_X); self.h_vel[e, i] = 0.0; self.h_goal[e, i] = (x, _abi.PARKED_X)
+            self.h_attr[e, i] = (0.3, 1.0)
 
 
 class HostStepIO(object):
@@ -219,3 +223,55 @@ def run_episodes(prm, N, seeds, rule='circle_crossing', gamma=0.9, robot_v_pref=
         step(prm, st, io, ep)
     assert not st.active.any()
     return ep, st
+
+
+def occupancy_maps(h_pos, h_vel, cell_num=4, cell_size=1.0, channels=3):
+    """MultiHumanRL.build_occupancy_maps (crowd_nav/policy/multi_human_rl.py:109-163) restated for [B][N][2] float64
+    position / velocity arrays -> [B][N][cell_num^2 * channels] float32. Plain float64 loops in the reference's
+    expression order (rotation into the human's velocity frame :121-129, floor to cell indices :132-138, per-cell mean
+    of the occupants' rotated velocities :143-160)."""
+    import math
+    h_pos = np.asarray(h_pos, dtype=np.float64); h_vel = np.asarray(h_vel, dtype=np.float64)
+    B, N = h_pos.shape[:2]
+    if N < 2:
+        raise ValueError('need at least one array to concatenate')
+    cells = cell_num * cell_num
+    out = np.zeros((B, N, cells * channels), dtype=np.float32)
+    for e in range(B):
+        for i in range(N):
+            angle = math.atan2(h_vel[e, i, 1], h_vel[e, i, 0])
+            lists = [([], []) for _ in range(cells)]
+            for j in range(N):
+                if j == i:
+                    continue
+                ox = h_pos[e, j, 0] - h_pos[e, i, 0]; oy = h_pos[e, j, 1] - h_pos[e, i, 1]
+                rot = math.atan2(oy, ox) - angle
+                dist = math.sqrt(ox * ox + oy * oy)
+                rx = math.cos(rot) * dist; ry = math.sin(rot) * dist
+                xi = math.floor(rx / cell_size + cell_num / 2); yi = math.floor(ry / cell_size + cell_num / 2)
+                if xi < 0 or xi >= cell_num or yi < 0 or yi >= cell_num:
+                    continue
+                vrot = math.atan2(h_vel[e, j, 1], h_vel[e, j, 0]) - angle
+                speed = math.sqrt(h_vel[e, j, 0] * h_vel[e, j, 0] + h_vel[e, j, 1] * h_vel[e, j, 1])
+                lists[cell_num * yi + xi][0].append(math.cos(vrot) * speed)
+                lists[cell_num * yi + xi][1].append(math.sin(vrot) * speed)
+            for c, (lx, ly) in enumerate(lists):
+                occ = len(lx) > 0
+                mx = sum(lx) / len(lx) if occ else 0.0
+                my = sum(ly) / len(ly) if occ else 0.0
+                if channels == 1:
+                    out[e, i, c] = 1.0 if occ else 0.0
+                elif channels == 2:
+                    out[e, i, 2 * c] = mx; out[e, i, 2 * c + 1] = my
+                else:
+                    out[e, i, 3 * c] = 1.0 if occ else 0.0; out[e, i, 3 * c + 1] = mx; out[e, i, 3 * c + 2] = my
+    return out
+
+
+def lookahead_humans(prm, st):
+    """The observation of env.onestep_lookahead (crowd_sim.py:414-416): one oracle step on a COPY of the state; the
+    humans' next states do not depend on the robot's action."""
+    cp = st.copy()
+    io = HostStepIO(st.B)
+    step(prm, cp, io)
+    return cp.h_pos.copy(), cp.h_vel.copy()

@@ -45,7 +45,7 @@ def _random_host_state(oracle, B, N, seed, spread=4.5):
     return st
 
 
-@pytest.mark.parametrize('name', ['circle5_invisible', 'square5_invisible', 'square20_invisible', 'circle5_visible'])
+@pytest.mark.parametrize('name', ['circle5_invisible', 'square5_invisible', 'square20_invisible', 'circle5_visible', 'mixed5_invisible'])
 def test_step_reproduces_golden_trajectories(cuda_env, oracle, name):
     """Each recorded reference step (pre-state, action, reward, info, post-state) is reproduced bit-exactly."""
     N, rule, vis, _ = SUITES[name]
@@ -59,7 +59,7 @@ def test_step_reproduces_golden_trajectories(cuda_env, oracle, name):
         torch.cuda.synchronize()
         dev = env.state.to_host()
         for e, s in enumerate(steps):
-            r, h = scene_arrays(s['post'])
+            r, h = scene_arrays(s['post'], N)
             assert (env.action_out[e].cpu().numpy() == [float(x) for x in s['action']]).all(), (name, case, e)
             assert float(env.reward[e]) == float(s['reward']) and int(env.done[e]) == int(s['done']) and int(env.info[e]) == s['info']
             if s['dmin'] is not None:
@@ -161,11 +161,11 @@ def test_full_suites_from_reference_scenes(cuda_env, oracle, name, generic):
         assert info[i] == c['info'] and steps[i] == c['steps'], (name, c['case'])
         assert t[i] == (25.0 if c['info'] == 4 else float(c['global_time']))
         assert ret[i] == float(c['return']) and tc[i] == c['too_close'] and mds[i] == float(c['min_dist_sum'])
-        r, h = scene_arrays(c['final'])
+        r, h = scene_arrays(c['final'], N)
         assert (frp[i] == r[:2]).all() and (hp[i] == h[:, :2]).all()
 
 
-@pytest.mark.parametrize('name', ['circle5_invisible', 'square5_invisible', 'square20_invisible', 'circle5_visible'])
+@pytest.mark.parametrize('name', ['circle5_invisible', 'square5_invisible', 'square20_invisible', 'circle5_visible', 'mixed5_invisible'])
 def test_full_suites_device_reset(cuda_env, name):
     """Same, but with scenes generated ON DEVICE from the case seeds (crowdsim_reset). Flags bit-exact, positions
     within 1e-5 (north_star bar; CUDA cos/sin may move initial coordinates by an ulp)."""
@@ -189,7 +189,8 @@ def test_full_suites_device_reset(cuda_env, name):
 def test_reset_matches_oracle(cuda_env, oracle):
     worst = 0
     for N, rule, rand in [(5, 'circle_crossing', False), (5, 'square_crossing', False), (20, 'square_crossing', False),
-                          (5, 'circle_crossing', True), (10, 'circle_crossing', False), (5, 'square_crossing', True)]:
+                          (5, 'circle_crossing', True), (10, 'circle_crossing', False), (5, 'square_crossing', True),
+                          (5, 'mixed', False), (5, 'mixed', True), (7, 'mixed', False)]:
         # NB: keep the packing feasible -- 10 humans with random radii up to 0.5 cannot all keep 1.2 m from each
         # other's starts AND goals on the r = 4 circle; the reference's rejection sampling would spin forever too.
         B = 2000
@@ -214,6 +215,16 @@ def test_reset_matches_oracle(cuda_env, oracle):
         if rule == 'square_crossing':        # no cos/sin on this path: bit-exact
             assert np.array_equal(dev['h_pos'], host.h_pos) and np.array_equal(dev['h_goal'], host.h_goal)
     print('worst abs difference of initial coordinates:', worst)
+
+
+def test_mixed_rule_counts(cuda_env):
+    """Rule `mixed`: per-scene human count follows the reference's distribution (crowd_sim.py:105-106; a static scene with
+    zero humans holds one dummy) -- checked against the fixture's counts for the same seeds."""
+    cases = load_golden('suite_mixed5_invisible')['cases']
+    env = cuda_env(len(cases), 5, 'mixed')
+    env.reset('test', cases=[c['case'] for c in cases])
+    torch.cuda.synchronize()
+    assert env.human_counts().cpu().tolist() == [len(c['init']['humans']) for c in cases]
 
 
 def test_reset_mask_and_active(cuda_env, oracle):
@@ -373,3 +384,48 @@ def test_autoreset_device_prefetch_reproduces_suite(cuda_env, slots):
     assert [int(x) for x in steps] == [c['steps'] for c in cases]
     fr = np.array([scene_arrays(c['final'])[0][:2] for c in cases])
     assert np.abs(frp - fr).max() < 1e-5
+
+
+def test_lookahead_humans_matches_oracle(cuda_env, oracle):
+    """crowdsim_lookahead_humans = the `ob` of env.onestep_lookahead (crowd_sim.py:414-416): bit-exact against one oracle
+    step on a copy of the state, small and large crowds, robot visible or not; the live state is untouched."""
+    for N, vis in ((5, 0), (5, 1), (2, 1), (20, 0)):
+        B = 700
+        host = _random_host_state(oracle, B, N, seed=40 + N)
+        env = cuda_env(B, N, robot_visible=bool(vis), robot_policy='external_xy')
+        env.state.load_host(host)
+        npos, nvel = env.lookahead_humans()
+        torch.cuda.synchronize()
+        o_pos, o_vel = oracle.lookahead_humans(oracle.default_params(robot_visible=vis, robot_policy=0), host)
+        assert np.array_equal(npos.cpu().numpy(), o_pos) and np.array_equal(nvel.cpu().numpy(), o_vel), (N, vis)
+        _assert_state_equal(env, host, what='state untouched')
+
+
+def test_occupancy_maps_match_reference_and_oracle(cuda_env, oracle):
+    """crowdsim_occupancy_maps vs (a) the reference's own build_occupancy_maps outputs (fixtures), (b) the oracle on random
+    batches. Occupancy pattern identical, mean velocities to 1e-6 (float64 trig of CUDA vs glibc differs in the last ulp)."""
+    rows = load_golden('occupancy_maps')['rows']
+    for r in rows:
+        h = np.array([[float(v) for v in hh] for hh in r['humans']])
+        ref = np.array([[float(v) for v in m] for m in r['maps']], dtype=np.float32)
+        env = cuda_env(1, h.shape[0])
+        pos = torch.from_numpy(h[None, :, 0:2].copy()).to(env.device); vel = torch.from_numpy(h[None, :, 2:4].copy()).to(env.device)
+        got = env.occupancy_maps(pos, vel, r['cell_num'], float(r['cell_size']), r['channels'])[0].cpu().numpy()
+        assert np.array_equal(got != 0, ref != 0), r['tag']
+        assert np.abs(got - ref).max() <= 1e-6, r['tag']
+    rng = np.random.RandomState(3)
+    for N in (2, 5, 20):
+        B = 300
+        pos = rng.uniform(-2.5, 2.5, (B, N, 2)); vel = rng.uniform(-1, 1, (B, N, 2))
+        vel[::7, 0] = 0.0                                            # standing humans
+        env = cuda_env(B, N)
+        for ch in (1, 2, 3):
+            got = env.occupancy_maps(torch.from_numpy(pos).to(env.device), torch.from_numpy(vel).to(env.device), 4, 1.0, ch).cpu().numpy()
+            ref = oracle.occupancy_maps(pos, vel, 4, 1.0, ch)
+            assert (got != 0).sum() > 0                               # the maps are not empty
+            mism = (got != 0) != (ref != 0)
+            assert mism.sum() == 0, (N, ch, int(mism.sum()))
+            assert np.abs(got - ref).max() <= 1e-6
+    env = cuda_env(4, 1)
+    with pytest.raises(ValueError):
+        env.occupancy_maps()                                          # the reference raises for a single human too

@@ -57,6 +57,31 @@ def test_sarl_decisions_match_reference(cuda_env):
             assert [float(x) for x in r['sarl_action']] == [float(x) for x in act[e]], e
 
 
+def test_om_sarl_decisions_match_reference(cuda_env):
+    """OM-SARL (policy.config with_om = true): the reference's own per-action values and greedy action, seed-0 weights,
+    against lookahead_pack + lookahead_humans + occupancy_maps + the same network on device."""
+    from crowdnav_b200.policy import make_sarl
+    o = load_golden('occupancy_maps')['om_sarl']
+    rows = o['decisions']
+    import pyoracle
+    host = fill_host_state(pyoracle, [r['scene'] for r in rows], 5)
+    host.g_time[:] = [float(r['global_time']) for r in rows]
+    env = cuda_env(len(rows), 5, robot_policy='external_xy')
+    env.state.load_host(host)
+    pol = make_sarl(gamma=o['gamma'], seed=o['seed'], with_om=True, cell_num=o['cell_num'], cell_size=float(o['cell_size']),
+                    om_channel_size=o['om_channel_size'])
+    assert pol.model.mlp1[0].in_features == 13 + 48
+    pol.set_device(env.device)
+    act = pol.act_batch(env).cpu().numpy()
+    vals = pol.action_values.cpu().numpy()
+    for e, r in enumerate(rows):
+        ref = np.array([float(v) for v in r['values']])
+        assert np.abs(vals[e] - ref).max() < 1e-4, e
+        top2 = np.sort(ref)[-2:]
+        if top2[1] - top2[0] > 1e-3:
+            assert [float(x) for x in r['action']] == [float(x) for x in act[e]], e
+
+
 def test_sarl_rollout_terminates_and_classifies(cuda_env):
     """BASELINE config 3 shape (SARL rollout through run_k_episodes): random-init weights, every episode ends in one of
     the three terminal classes, bookkeeping is consistent."""

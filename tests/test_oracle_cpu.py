@@ -59,7 +59,7 @@ def test_batched_c_oracle_reproduces_reference_python(oracle, name):
         assert ep.res_return[i] == float(c['return'])
         assert ep.res_too_close[i] == c['too_close']
         assert ep.res_min_dist_sum[i] == float(c['min_dist_sum'])
-        r, h = scene_arrays(c['final'])
+        r, h = scene_arrays(c['final'], N)
         assert (ep.res_final_rpos[i] == r[:2]).all()
         assert (st.h_pos[i] == h[:, :2]).all() and (st.h_vel[i] == h[:, 2:4]).all()
 
@@ -73,7 +73,7 @@ def test_reset_scenes_match_reference(oracle):
         st = oracle.HostState(len(rows), N)
         oracle.reset(st, [r['seed'] for r in rows], kw['test_sim'], randomize_attributes=kw.get('randomize', False))
         for e, row in enumerate(rows):
-            r, h = scene_arrays(row['scene'])
+            r, h = scene_arrays(row['scene'], N)
             assert (st.r_pos[e] == r[0:2]).all() and (st.r_goal[e] == r[4:6]).all() and st.r_theta[e] == r[8], name
             assert (st.h_pos[e] == h[:, 0:2]).all() and (st.h_goal[e] == h[:, 4:6]).all(), (name, row['case'])
             assert (st.h_attr[e] == h[:, 6:8]).all(), name
@@ -81,7 +81,7 @@ def test_reset_scenes_match_reference(oracle):
 
 def test_trajectory_steps_match_reference(oracle):
     """Every recorded step of the golden trajectories: pre-state -> one oracle step == recorded post-state."""
-    for name in ('circle5_invisible', 'square5_invisible', 'square20_invisible', 'circle5_visible'):
+    for name in ('circle5_invisible', 'square5_invisible', 'square20_invisible', 'circle5_visible', 'mixed5_invisible'):
         N, rule, vis, _ = SUITES[name]
         d = load_golden('traj_' + name)
         prm = oracle.default_params(robot_visible=vis)
@@ -91,7 +91,7 @@ def test_trajectory_steps_match_reference(oracle):
             io = oracle.HostStepIO(len(steps))
             oracle.step(prm, st, io)
             for e, s in enumerate(steps):
-                r, h = scene_arrays(s['post'])
+                r, h = scene_arrays(s['post'], N)
                 assert (io.action_out[e] == [float(x) for x in s['action']]).all()
                 assert io.reward[e] == float(s['reward']) and io.done[e] == s['done'] and io.info[e] == s['info']
                 if s['dmin'] is not None:
@@ -250,3 +250,19 @@ def test_rvo2_shim_vs_batched_oracle_random_crowds(oracle, N):
         sim.setAgentPrefVelocity(0, tuple(g / speed if speed > 1 else g))
         sim.doStep()
         assert sim.getAgentVelocity(0) == (act[0], act[1]), (N, trial)
+
+
+def test_occupancy_maps_match_reference(oracle):
+    """oracle.occupancy_maps vs the reference's MultiHumanRL.build_occupancy_maps (multi_human_rl.py:109-163) on recorded
+    scenes, lookahead states and random crowds, 3 grid configurations x 3 channel modes. The occupancy pattern must be
+    identical; mean velocities agree to float32 rounding (the reference sums Python floats, then casts to float32)."""
+    rows = load_golden('occupancy_maps')['rows']
+    assert len(rows) > 100
+    for r in rows:
+        h = np.array([[float(v) for v in hh] for hh in r['humans']])
+        ref = np.array([[float(v) for v in m] for m in r['maps']], dtype=np.float32)
+        got = oracle.occupancy_maps(h[None, :, 0:2], h[None, :, 2:4], r['cell_num'], float(r['cell_size']), r['channels'])[0]
+        assert got.shape == ref.shape, r['tag']
+        assert np.array_equal(got != 0, ref != 0), r['tag']
+        assert np.abs(got - ref).max() <= 1e-6, r['tag']
+    assert any(np.array(r['maps'], dtype=np.float64).any() for r in rows)

@@ -20,12 +20,22 @@ SUITES = {
     'circle5_visible': (5, 'circle_crossing', 1, False),
     'circle10_visible': (10, 'circle_crossing', 1, False),
     'circle5_random_attr': (5, 'circle_crossing', 0, True),
+    'mixed5_invisible': (5, 'mixed', 0, False),      # 1..5 humans per case; unused slots are parked (crowdsim_b200.h)
 }
 
+PARKED_X = 1.0e6
 
-def scene_arrays(scene):
+
+def scene_arrays(scene, N=None):
+    """robot [9], humans [n][8] (px,py,vx,vy,gx,gy,radius,v_pref). With N: padded to N rows with PARKED humans, the
+    fixed-N layout's stand-in for humans a `mixed` scene does not have."""
     r = np.array([float(x) for x in scene['robot']])
-    h = np.array([[float(x) for x in row] for row in scene['humans']])
+    rows = [[float(x) for x in row] for row in scene['humans']]
+    if N is not None:
+        for i in range(len(rows), N):
+            x = PARKED_X + 100.0 * i
+            rows.append([x, PARKED_X, 0.0, 0.0, x, PARKED_X, 0.3, 1.0])
+    h = np.array(rows)
     return r, h
 
 
