@@ -8,7 +8,7 @@ from crowdnav_b200.batched import BatchedCrowdSim, default_config
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 rule = sys.argv[2] if len(sys.argv) > 2 else 'circle_crossing'
-B, pools, K = 4096, (64 if N <= 5 else 16), 400
+B, pools, K, PE = 4096, (64 if N <= 5 else 16), 1600, 4     # PE: prefetch on every 4th visit of a batch, like bench.py
 envs = []
 for p in range(pools):
     env = BatchedCrowdSim(B); env.configure(default_config(human_num=N, test_sim=rule, train_val_sim=rule)); env.set_robot_policy('orca')
@@ -18,6 +18,8 @@ for p in range(pools):
 torch.cuda.synchronize()
 for t in range(K):
     env = envs[t % pools]
-    env.step(); env.prefetch()
+    env.step()
+    if (t // pools) % PE == 0:
+        env.prefetch()
 torch.cuda.synchronize()
 print('done', K)

@@ -8,9 +8,9 @@ echo "== pytest -m gpu" ; timeout 900 python -m pytest tests -m gpu -x -q --time
 echo "== bench" ; timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
 echo "== bench reference" ; timeout 600 python bench.py --impl reference --steps 200 --warmup 20 > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err; cat gpurun_out/bench_ref.json
 echo "== ncu launch list (eager launches of the same step/prefetch sequence)"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"step_|scene_|lookahead|pack_" -s 300 -c 400 --csv --log-file gpurun_out/launches.csv python scripts/eager_loop.py > gpurun_out/ncu_list.log 2>&1; tail -2 gpurun_out/ncu_list.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"step_|scene_|lookahead|pack_" -s 600 -c 800 --csv --log-file gpurun_out/launches.csv python scripts/eager_loop.py > gpurun_out/ncu_list.log 2>&1; tail -2 gpurun_out/ncu_list.log
 echo "== ncu full on the step kernel"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:step_flat -s 200 -c 2 -o gpurun_out/prof_step python scripts/eager_loop.py > gpurun_out/ncu_full.log 2>&1; tail -2 gpurun_out/ncu_full.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:step_flat -s 300 -c 2 -o gpurun_out/prof_step python scripts/eager_loop.py > gpurun_out/ncu_full.log 2>&1; tail -2 gpurun_out/ncu_full.log
 
 echo "== latency probe (mid-episode states)" ; ./build_probe/probe 12 | tee gpurun_out/latency_probe.txt
 echo "== configs 1/3/4" ; timeout 600 python scripts/measure_misc.py | tee gpurun_out/measure_misc.json
