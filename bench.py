@@ -166,6 +166,9 @@ def cpu_oracle_rate(args, seconds=12.0):
         n_total, B, time.perf_counter() - t_begin, rates[0], rates[-1])
 
 
+WORKLOAD = '%d batched envs x %d ORCA humans, %s, ORCA robot (invisible), auto-reset, per GPU'
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path = oracle port (the reference is Python + an
     absent native rvo2; it cannot travel to the GPU box), all host threads, same config/metric."""
@@ -206,7 +209,8 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'env-steps/s', 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f64 state + f32 ORCA solver', 'data': 'synthetic',
-            'config': {'workload': '%d batched envs x %d ORCA humans, %s, ORCA robot (invisible), auto-reset' % (B, N, args.rule)},
+            'config': {'workload': WORKLOAD % (B, N, args.rule), 'envs_per_gpu': B, 'humans': N,
+                       'note': 'CPU arm: one 4096-env batch stepped in lockstep by all host threads (rank 0 only)'},
             'cpu_baseline': {'value': v, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
                              'sample': '%d lockstep passes over a %d-env batch per run; C restatement of the reference loop '
                                        '(oracle/crowdsim_oracle.c, OpenMP over envs, thread count calibrated, host has %d logical CPUs)' % (args.steps, B, os.cpu_count() or 0)},
@@ -496,7 +500,7 @@ def run_ours(args):
         line = {'metric': METRIC, 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': K, 'warmup': max(W, 3),
                 'ms_per_step': ms_max / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'f64 state + f32 ORCA solver', 'data': 'synthetic',
-                'config': {'workload': '%d batched envs x %d ORCA humans, %s, ORCA robot (invisible), auto-reset, per GPU' % (B, N, args.rule),
+                'config': {'workload': WORKLOAD % (B, N, args.rule),
                            'envs_per_gpu': B, 'humans': N, 'l2': 'inputs larger than L2: %d rotating independent batches = %.0f MB of state' % (pools, pools * B * bytes_per_env / 1e6),
                            'batches_in_flight': LANES,
                            'parallelism': 'independent envs sharded over %d GPU(s), no data-path collective' % world},

@@ -91,10 +91,12 @@ ORCA_HD __forceinline__ void lp1_all(const RegLines<M> &R, const bool (&valid)[M
             const float num = det(R.d[j], lp - R.p[j]);
             const bool use = valid[j];
             const bool par = fabsf(den) <= kEps;
-            // absent positions hold zero lines (den = 0) and parallel lines have |den| <= eps: dividing by them sends the whole
-            // warp through the IEEE division slow path (ncu, 262144 envs: 10 slow-path calls per warp = 9 % of all
-            // instructions). t is only consumed when (use && !par), so those lanes divide by 1 instead.
-            const float t = num / ((use && !par) ? den : 1.0f);
+            // absent positions hold zero lines (num = den = 0) and parallel lines have |den| <= eps: an IEEE division with a
+            // zero numerator or denominator sends the whole warp through the division slow path (ncu: 10 slow-path calls
+            // per warp = 8-9 % of all executed instructions). t is only consumed when (use && !par), so the other lanes
+            // divide 1 by 1 instead.
+            const bool live_pair = use && !par;
+            const float t = (live_pair ? num : 1.0f) / (live_pair ? den : 1.0f);
             bad = bad || (use && par && num < 0.0f);
             const bool right = use && !par && den >= 0.0f, leftb = use && !par && den < 0.0f;
             t_right = (right && t < t_right) ? t : t_right;          // std::min(tRight, t)
