@@ -12,5 +12,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"
 echo "== ncu full on the step kernel"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:step_flat -s 300 -c 2 -o gpurun_out/prof_step python scripts/eager_loop.py > gpurun_out/ncu_full.log 2>&1; tail -2 gpurun_out/ncu_full.log
 
+echo "== ncu full on the step kernel at full occupancy (262144 envs, mid-episode)"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:step_flat -s 14 -c 1 -o gpurun_out/prof_step_big python scripts/eager_big.py > gpurun_out/ncu_big.log 2>&1; tail -2 gpurun_out/ncu_big.log
 echo "== latency probe (mid-episode states)" ; ./build_probe/probe 12 | tee gpurun_out/latency_probe.txt
 echo "== configs 1/3/4" ; timeout 600 python scripts/measure_misc.py | tee gpurun_out/measure_misc.json

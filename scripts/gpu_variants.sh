@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B of prebuilt library variants (build_probe/lib_*.so, built in the dev container) through bench.py.
 mkdir -p gpurun_out
-for v in default wpb2 wpb1 mb7 mb5 wpb2_mb7; do
+for v in ${VARIANTS:-default wpb8}; do
   if [ $v = default ]; then unset CROWDSIM_B200_LIB; else export CROWDSIM_B200_LIB=$PWD/build_probe/lib_$v.so; fi
   timeout 600 python bench.py --no-cpu-baseline --e2e-batches 4 2>gpurun_out/var_$v.err > gpurun_out/var_$v.json || tail -3 gpurun_out/var_$v.err
   python - <<PY
