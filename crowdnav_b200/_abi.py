@@ -87,7 +87,7 @@ def declare(lib, prefix='crowdsim_', with_stream=True):
     return lib
 
 
-EXPORTS = ('crowdsim_abi_version', 'crowdsim_device_check', 'crowdsim_launch_count', 'crowdsim_debug_force_generic', 'crowdsim_graph_launch',
+EXPORTS = ('crowdsim_abi_version', 'crowdsim_device_check', 'crowdsim_launch_count', 'crowdsim_debug_force_generic', 'crowdsim_debug_lp3_queue', 'crowdsim_graph_launch',
            'crowdsim_event_wait', 'crowdsim_step',
            'crowdsim_orca_act', 'crowdsim_reset', 'crowdsim_prefetch_scenes', 'crowdsim_pack_joint', 'crowdsim_lookahead_pack',
            'crowdsim_lookahead_humans', 'crowdsim_occupancy_maps')
@@ -118,6 +118,8 @@ def load():
         lib.crowdsim_launch_count.restype = C.c_ulonglong
         lib.crowdsim_debug_force_generic.argtypes = [C.c_int]
         lib.crowdsim_debug_force_generic.restype = None
+        lib.crowdsim_debug_lp3_queue.argtypes = [C.c_int]
+        lib.crowdsim_debug_lp3_queue.restype = None
         lib.crowdsim_graph_launch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.crowdsim_graph_launch.restype = C.c_int
         lib.crowdsim_event_wait.argtypes = [C.c_void_p]

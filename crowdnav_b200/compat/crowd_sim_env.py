@@ -34,7 +34,7 @@ class CrowdSim(object):
         self.randomize_attributes = None; self.train_val_sim = None; self.test_sim = None
         self.square_width = None; self.circle_radius = None; self.human_num = None
         self.states = None; self.action_values = None; self.attention_weights = None
-        self._engine = None
+        self._engine = None; self._config_human_num = None
 
     # ---- crowd_sim.py:51-79 ----
     def configure(self, config):
@@ -46,6 +46,7 @@ class CrowdSim(object):
                   'discomfort_penalty_factor', 'case_capacity', 'case_size', 'train_val_sim', 'test_sim', 'square_width',
                   'circle_radius', 'human_num', 'case_counter'):
             setattr(self, a, getattr(eng, a))
+        self._config_human_num = eng.human_num
         logging.info('human number: {}'.format(self.human_num))
         logging.info("Randomize human's radius and preferred speed" if self.randomize_attributes
                      else "Not randomize human's radius and preferred speed")
@@ -81,17 +82,28 @@ class CrowdSim(object):
         if test_case is not None:
             self.case_counter[phase] = test_case
         multi = getattr(self.robot.policy, 'multiagent_training', True)
-        if not multi and phase in ('train', 'val'):
-            raise NotImplementedError('single-human training scenes (crowd_sim.py:265-267,278) are not built yet')
         if not multi:
-            self.train_val_sim = 'circle_crossing'
+            self.train_val_sim = 'circle_crossing'            # crowd_sim.py:266-267
         self._sync_engine_config()
         eng = self._engine
         case = self.case_counter[phase]
         if case >= 0:
-            eng.reset(phase, cases=[case])
+            rule = self.test_sim if phase == 'test' else self.train_val_sim
+            # crowd_sim.py:277-281: policies trained on a single human (CADRL) get one-human train / val scenes; rule
+            # `mixed` draws up to 5 humans whatever human_num says (crowd_sim.py:103-115)
+            n_slots = 1 if (phase in ('train', 'val') and not multi) else self._config_human_num
+            if rule == 'mixed':
+                n_slots = max(n_slots, 5)
+            if eng.human_num != n_slots:
+                eng.human_num = n_slots; eng._alloc()
+            eng.reset(phase, cases=[case], rule=rule)
             self.case_counter[phase] = (case + 1) % self.case_size[phase]
-            n = self.human_num
+            n = n_slots
+            if rule == 'mixed':
+                n = int(eng.human_counts()[0])                # present humans; the other slots are parked (crowdsim_b200.h)
+                s = eng.state
+                dummy = (n == 1 and s.h_pos[0, 0].tolist() == [0.0, -10.0] and s.h_goal[0, 0].tolist() == [0.0, -10.0])
+                self.human_num = 0 if dummy else n            # crowd_sim.py:115 (a static scene with 0 humans keeps one dummy)
         else:
             assert phase == 'test'
             if case != -1:

@@ -18,6 +18,7 @@ namespace cs {
 
 unsigned long long g_launches = 0;
 int g_force_generic = 0;   // test hook: route every N through the generic one-thread-per-agent kernel
+int g_lp3_queue = -1;      // test / tuning hook: -1 = pick the small-crowd kernel's lp3 queue by grid size, 0 = per block, 1 = per warp
 
 struct StepArgs {
     KParams k;
@@ -250,7 +251,7 @@ static int launch(const crowdsim_params *prm, int B, int N, const crowdsim_state
         // 3-5 % faster at 64 k - 1 M envs). Measured with scripts/gpu_ab_lp3.sh.
         static int n_sm = 0;
         if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148; }
-        const bool warpq = blocks * CS_FLAT_WPB <= 12 * n_sm;
+        const bool warpq = (g_lp3_queue < 0) ? (blocks * CS_FLAT_WPB <= 12 * n_sm) : (g_lp3_queue == 1);
         #define CS_FLAT_LAUNCH(NN) do { if (warpq) step_flat_kernel<NN, 99, true><<<blocks, 32 * CS_FLAT_WPB, 0, stream>>>(A); \
                                         else step_flat_kernel<NN, 99, false><<<blocks, 32 * CS_FLAT_WPB, 0, stream>>>(A); } while (0)
         switch (N) {
@@ -306,6 +307,8 @@ extern "C" int crowdsim_event_wait(void *event)
 }
 
 extern "C" void crowdsim_debug_force_generic(int on) { cs::g_force_generic = on; }
+
+extern "C" void crowdsim_debug_lp3_queue(int mode) { cs::g_lp3_queue = mode; }
 
 extern "C" int crowdsim_abi_version(void) { return CROWDSIM_ABI_VERSION; }
 

@@ -192,6 +192,8 @@ unsigned long long crowdsim_launch_count(void);
 /* Test hook: 1 = use the generic one-thread-per-agent step kernel for every N (default 0: N <= 5 uses the
  * register-resident small-crowd kernel). Both are held to the same bit-exact parity bar. */
 void crowdsim_debug_force_generic(int on);
+/* Test / tuning hook for the small-crowd kernel's linearProgram3 queue: -1 (default) = by grid size, 0 = per block, 1 = per warp. */
+void crowdsim_debug_lp3_queue(int mode);
 
 /* Host plumbing for callers that keep several env batches in flight from an interpreter (batched.HostStepper.launch /
  * wait; the reference's loop blocks in env.step, crowd_nav/utils/explorer.py:42-43): replay a captured CUDA graph

@@ -84,3 +84,41 @@ def test_debug_scene_minus_one():
     for _ in range(5):
         ob, reward, done, info = env.step(robot.act(ob))
         assert env.humans[1].px == -env.humans[2].px and robot.px == 0.0     # mirror symmetry is preserved exactly
+
+
+def test_mixed_rule_episodes_match_reference():
+    """test_sim = 'mixed' through the single-env surface: per case the number of humans, terminal class, step count and
+    final robot position of the reference's recorded episodes (the list of humans shrinks / grows per episode like the
+    reference's; here that does not raise -- the reference's own step() does)."""
+    cases = load_golden('suite_mixed5_invisible')['cases'][:14]
+    env, robot = _make(test_sim='mixed')
+    code = {'ReachGoal': 2, 'Collision': 3, 'Timeout': 4}
+    for c in cases:
+        ob = env.reset('test', c['case'])
+        assert len(ob) == len(env.humans) == len(c['init']['humans']), c['case']
+        _, h0 = scene_arrays(c['init'])
+        assert np.abs(np.array([[h.px, h.py, h.gx, h.gy] for h in env.humans]) - h0[:, [0, 1, 4, 5]]).max() < 1e-12
+        done, steps = False, 0
+        while not done:
+            ob, reward, done, info = env.step(robot.act(ob))
+            steps += 1
+        assert code[type(info).__name__] == c['info'] and steps == c['steps'], c['case']
+        r, _ = scene_arrays(c['final'])
+        assert abs(robot.px - r[0]) < 1e-9 and abs(robot.py - r[1]) < 1e-9
+
+
+def test_single_human_training_scenes(oracle):
+    """crowd_sim.py:266-267,277-279: a policy with multiagent_training = False (CADRL) gets ONE-human circle-crossing
+    scenes in the train / val phases (seed = 2000 + case / 0 + case), the full crowd in the test phase."""
+    env, robot = _make(human_num=5, test_sim='square_crossing')
+    robot.policy.multiagent_training = False
+    for phase, offset, case in (('train', 2000, 7), ('val', 0, 3)):
+        ob = env.reset(phase, case)
+        assert len(ob) == 1 and len(env.humans) == 1 and env.train_val_sim == 'circle_crossing'
+        host = oracle.HostState(1, 1)
+        oracle.reset(host, [offset + case], 'circle_crossing')
+        assert abs(env.humans[0].px - host.h_pos[0, 0, 0]) < 1e-12 and abs(env.humans[0].py - host.h_pos[0, 0, 1]) < 1e-12
+        ob, reward, done, info = env.step(robot.act(ob))
+        assert len(ob) == 1
+    ob = env.reset('test', 0)
+    assert len(ob) == 5 and len(env.humans) == 5
