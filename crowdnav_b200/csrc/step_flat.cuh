@@ -9,15 +9,18 @@
 // the LP code has static register indexing, no local/shared memory traffic and instruction-level parallelism
 // across the independent (i, j) line pairs.
 // linearProgram3 (needed by ~4.6 % of the solves, i.e. by some lane of ~3 of 4 warps) is NOT run in place: the
-// solves that need it are compacted into a block-level shared-memory queue. Inside linearProgram3 the sub-problem of
-// each line i (linearProgram2 over the lines projected onto i, started from optVelocity * radius) depends only on the
-// lines, not on the running result, so the <= N-1 sub-problems of a queued solve run on N-1 LANES IN PARALLEL (the
-// sequential shared-memory LP code of orca_device.cuh), followed by a 4-step scan. Before this, the pass was a
-// ~1500-instruction serial chain on a handful of lanes with the whole block waiting: ~4.5 of 14 us per launch.
+// solves that need it are compacted into a shared-memory queue. Inside linearProgram3 the sub-problem of each line i
+// (linearProgram2 over the lines projected onto i, started from optVelocity * radius) depends only on the lines, not
+// on the running result, so the <= N-1 sub-problems of a queued solve run on N-1 LANES IN PARALLEL (the sequential
+// shared-memory LP code of orca_device.cuh), followed by a 4-step scan. Before this, the pass was a ~1500-instruction
+// serial chain on a handful of lanes with the whole block waiting: ~4.5 of 14 us per launch.
+// The queue is per BLOCK (WARPQ = false: one warp runs the pass for the whole block, the others wait at a barrier;
+// fewest instructions, best when the launch fills the chip) or per WARP (WARPQ = true: no block barrier, every warp runs
+// the pass for its own 1-2 solves; best for launches that leave the SMs mostly empty). cs::launch() picks by grid size.
 //
 // Evidence that motivated this design (profiles/r01_*): one-thread-per-agent with shared-memory lines ran at 13.6/32
 // active lanes and 3480 instructions per warp; the warp-per-env cooperative variant needed 1750 warp instructions
-// per env. This kernel needs ~300 per env.
+// per env. This kernel needs 483 per env (2.4 k per warp of 5 envs) at 23/32 active lanes.
 #pragma once
 #include "crowdsim_common.cuh"
 #include "orca_spec.cuh"
@@ -26,12 +29,13 @@ namespace cs {
 
 #define CS_FULL 0xffffffffu
 
-// EPW = 32 / (N + 1) whole envs per warp (dense packing; sparser packings were measured and are never faster, see
-// step_kernel.cu: flat_pick_epw). STAGE is a profiling aid (scripts/latency_probe.cu instantiates cut-down variants to
+// EPW = 32 / (N + 1) whole envs per warp (dense packing; sparser packings were measured and are never faster,
+// profiles/r01_tune_epw_n5.txt). STAGE is a profiling aid (scripts/latency_probe.cu instantiates cut-down variants to
 // attribute latency); the library only instantiates the full kernel (STAGE = 99).
 // Register budget: asking for 6 resident blocks per SM (<= 80 registers, a few bytes of spill) is neutral at 4096 envs and
 // 9 % faster at 65 k .. 1 M envs than the unconstrained 90-register build (scripts/latency_probe.cu, -DCS_FLAT_MINBLOCKS=1/6/8).
-// Warps per block (block = CS_FLAT_WPB * 32 threads) and the resident-blocks hint that goes with it.
+// CS_FLAT_WPB = warps per block, CS_FLAT_MINBLOCKS = resident-blocks hint (per 128 threads), CS_FLAT_WARP_LP3 = default of the
+// WARPQ template parameter: build-time knobs for A/B runs (scripts/gpu_variants.sh); 4 / 6 / size-dependent were kept.
 #ifndef CS_FLAT_WPB
 #define CS_FLAT_WPB 4
 #endif
