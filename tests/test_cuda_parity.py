@@ -356,18 +356,19 @@ def test_autoreset_install_bit_exact(cuda_env, oracle):
             assert np.array_equal(getattr(ep, f).cpu().numpy(), getattr(hep, f)), f
 
 
-@pytest.mark.parametrize('slots', [64, 500])
-def test_autoreset_device_prefetch_reproduces_suite(cuda_env, slots):
+@pytest.mark.parametrize('slots,suite', [(64, 'circle5_invisible'), (500, 'circle5_invisible'), (48, 'mixed5_invisible')])
+def test_autoreset_device_prefetch_reproduces_suite(cuda_env, slots, suite):
     """Full device pipeline: scenes prefetched ON DEVICE from the shared case queue (side stream), installed by the step
-    kernel. 500 test cases through `slots` slots: terminal class and step count exact, final position within 1e-5."""
-    N = 5
-    cases = load_golden('suite_circle5_invisible')['cases']
+    kernel. All test cases of the suite through `slots` slots: terminal class and step count exact, final position
+    within 1e-5. (`mixed`: scenes with 1..5 humans, the other slots parked, stream through the same pipeline.)"""
+    N, rule, _, _ = SUITES[suite]
+    cases = load_golden('suite_' + suite)['cases']
     k = len(cases)
-    env = cuda_env(slots, N)
+    env = cuda_env(slots, N, rule)
     ep = env.track_episodes(k)
     env.set_case_queue(0, k, 'test')
-    env.enable_autoreset('circle_crossing')
-    env.reset_seeds(rule='circle_crossing', use_queue=True)
+    env.enable_autoreset(rule)
+    env.reset_seeds(rule=rule, use_queue=True)
     side = torch.cuda.Stream()
     for it in range(4000):
         if it % 2 == 0:
