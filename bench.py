@@ -79,6 +79,13 @@ class ClockSampler(object):
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), [x.strip() for x in line.split(',')]))
 
+    def wait_ready(self, timeout=20.0):
+        """Block until the child has delivered its first sample (nvidia-smi can take seconds to start on a cold box)."""
+        t_end = time.perf_counter() + timeout
+        while not self.rows and time.perf_counter() < t_end and self.proc is not None and self.proc.poll() is None:
+            time.sleep(0.01)
+        return bool(self.rows)
+
     def mark_start(self):
         self.t0 = time.perf_counter()
 
@@ -234,6 +241,7 @@ def run_ours(args):
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
+    sampler = ClockSampler(local)                            # started early: its start-up must be over before the timed region
     lib = _abi.load()
     lib.crowdsim_debug_lp3_queue({'auto': -1, 'block': 0, 'warp': 1}[args.lp3_queue])
     B, N, K, W = args.envs, args.humans, args.steps, args.warmup
@@ -322,11 +330,11 @@ def run_ours(args):
             n = int(min(env._case_counter.item(), env.k_total))
             tot += int(env.episodes.res_steps[:n].sum().item()) + int((env.episodes.ep_steps * env.state.active.to(torch.int32)).sum().item())
         return tot
-    sampler = ClockSampler(local)
     with torch.cuda.stream(main):
         g_warm.replay()
     barrier()
     steps_before = env_steps_done()
+    sampler.wait_ready()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.mark_start()
     with torch.cuda.stream(main):
