@@ -9,6 +9,11 @@ kernel (6 ORCA solves/env, collision/reward/terminal, integration, episode bookk
 of the scenes of envs whose episode just ended (fresh MT19937 seeds), so every env is live on every step.
 Because 4096 envs of state are only 2.6 MB, the bench rotates through POOLS independent batches whose combined state
 exceeds the 126 MB L2 ("inputs larger than L2"); the batch touched by a step was last touched POOLS steps ago.
+The timed region is ONE CUDA graph of K step launches (+ one scene-prefetch launch per batch on every 4th visit, side
+streams); batch p always runs on stream p mod S (--streams, default 16), so the steps of one batch stay ordered while
+independent batches overlap on the device. `value` = env-steps PERFORMED (counted by the step kernel) / device time;
+`single_stream` = the same with one batch in flight; `e2e` = HostStepper.launch()/wait() over 16 batches with pinned host
+buffers in and out on every batch-step; `roofline` = the step kernel alone (single-stream graph, CUDA events).
 
 Printed JSON keys follow the driver contract; see DESIGN.md "Measurement" for definitions. The oracle (oracle/) is
 executed here ONLY in the cpu_baseline leg and in --impl reference.
