@@ -36,6 +36,14 @@ namespace cs {
 // 9 % faster at 65 k .. 1 M envs than the unconstrained 90-register build (scripts/latency_probe.cu, -DCS_FLAT_MINBLOCKS=1/6/8).
 // CS_FLAT_WPB = warps per block, CS_FLAT_MINBLOCKS = resident-blocks hint (per 128 threads), CS_FLAT_WARP_LP3 = default of the
 // WARPQ template parameter: build-time knobs for A/B runs (scripts/gpu_variants.sh); 4 / 6 / size-dependent were kept.
+// EXPERIMENT: -DCS_FLAT_NO_ROT compiles the unicycle-robot trigonometry out of the small-crowd kernel
+// (~12 % of its SASS, never executed by holonomic robots) to measure what the instruction-fetch stalls cost; such a build
+// only serves holonomic / ORCA robots. Default: runtime test, as the reference's agent.py:115-135.
+#ifdef CS_FLAT_NO_ROT
+#define CS_FLAT_IS_ROT(k) false
+#else
+#define CS_FLAT_IS_ROT(k) ((k).robot_policy == CROWDSIM_ROBOT_EXTERNAL_ROT)
+#endif
 #ifndef CS_FLAT_WPB
 #define CS_FLAT_WPB 4
 #endif
@@ -83,7 +91,7 @@ __global__ void __launch_bounds__(32 * CS_FLAT_WPB, CS_FLAT_MINBLOCKS * 4 / CS_F
         } else {
             pos = ld2(A.st.r_pos, e); vel = ld2(A.st.r_vel, e); goal = ld2(A.st.r_goal, e); attr = ld2(A.st.r_attr, e);
             gtime = A.st.g_time[e];
-            if (k.robot_policy == CROWDSIM_ROBOT_EXTERNAL_ROT) theta = A.st.r_theta[e];
+            if (CS_FLAT_IS_ROT(k)) theta = A.st.r_theta[e];
             if (k.robot_policy != CROWDSIM_ROBOT_ORCA) ext = ld2(A.io.action, e);
             if (A.has_ep) { ep_t = A.ep.ep_steps[e]; ep_ret = A.ep.ep_return[e]; ep_tc = A.ep.ep_too_close[e]; ep_mds = A.ep.ep_min_dist_sum[e]; ep_c = A.ep.ep_case[e]; }
             if (A.has_ar) { slot_state = *reinterpret_cast<volatile uint8_t *>(A.ar.n_state + e); want_flag = A.ar.want[e]; }
@@ -287,7 +295,7 @@ __global__ void __launch_bounds__(32 * CS_FLAT_WPB, CS_FLAT_MINBLOCKS * 4 / CS_F
     double ax = 0, ay = 0, rvx = 0, rvy = 0;
     if (is_robot) {
         if (k.robot_policy == CROWDSIM_ROBOT_ORCA) { ax = (double)nv.x; ay = (double)nv.y; rvx = ax; rvy = ay; }
-        else if (k.robot_policy == CROWDSIM_ROBOT_EXTERNAL_ROT) { ax = ext.x; ay = ext.y; rvx = ax * cos(ay + theta); rvy = ax * sin(ay + theta); }
+        else if (CS_FLAT_IS_ROT(k)) { ax = ext.x; ay = ext.y; rvx = ax * cos(ay + theta); rvy = ax * sin(ay + theta); }
         else { ax = ext.x; ay = ext.y; rvx = ax; rvy = ay; }
     }
     const int rl = ebase + N;                                // my env's robot lane
@@ -318,7 +326,7 @@ __global__ void __launch_bounds__(32 * CS_FLAT_WPB, CS_FLAT_MINBLOCKS * 4 / CS_F
         bool done = false;
         if (live) {
             double npx, npy, nvx, nvy;
-            if (k.robot_policy != CROWDSIM_ROBOT_EXTERNAL_ROT) { npx = pos.x + ax * dt; npy = pos.y + ay * dt; nvx = ax; nvy = ay; }
+            if (!CS_FLAT_IS_ROT(k)) { npx = pos.x + ax * dt; npy = pos.y + ay * dt; nvx = ax; nvy = ay; }
             else { const double th = theta + ay; npx = pos.x + cos(th) * ax * dt; npy = pos.y + sin(th) * ax * dt; nvx = nvy = 0; }
             const bool reaching_goal = norm2(npx - goal.x, npy - goal.y) < attr.x;
             double reward; int info;
@@ -327,7 +335,7 @@ __global__ void __launch_bounds__(32 * CS_FLAT_WPB, CS_FLAT_MINBLOCKS * 4 / CS_F
             else if (reaching_goal) { reward = k.success_reward; done = true; info = CROWDSIM_INFO_REACHGOAL; }
             else if (dmin < k.discomfort_dist) { reward = (dmin - k.discomfort_dist) * k.discomfort_penalty_factor * dt; done = false; info = CROWDSIM_INFO_DANGER; }
             else { reward = 0; done = false; info = CROWDSIM_INFO_NOTHING; }
-            if (k.robot_policy == CROWDSIM_ROBOT_EXTERNAL_ROT) {
+            if (CS_FLAT_IS_ROT(k)) {
                 double nth = fmod(theta + ay, 2 * CS_PI); if (nth < 0) nth += 2 * CS_PI;
                 A.st.r_theta[e] = nth; nvx = ax * cos(nth); nvy = ax * sin(nth);
             }

@@ -9,5 +9,7 @@ S="crowdnav_b200/csrc/step_kernel.cu crowdnav_b200/csrc/reset_kernel.cu crowdnav
 build() { nvcc $F $2 $S -o build_probe/lib_$1.so & }
 build f32x2 "-DCS_F32X2"                       # packed FADD2/FMUL2 for the (x, y) arithmetic (unmeasured)
 build f32x2_mb5 "-DCS_F32X2 -DCS_FLAT_MINBLOCKS=5"
+build norot "-DCS_FLAT_NO_ROT"                   # unicycle code compiled out: only for holonomic / ORCA robots
+build norot_f32x2 "-DCS_FLAT_NO_ROT -DCS_F32X2"
 wait
 ls -la build_probe/*.so
