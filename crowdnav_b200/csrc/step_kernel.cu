@@ -248,7 +248,7 @@ static int launch(const crowdsim_params *prm, int B, int N, const crowdsim_state
         const int blocks = (B + epb - 1) / epb;
         // linearProgram3 queue: per warp when the launch leaves SMs mostly empty (latency-bound: no block barrier, 2-4 %
         // faster at 1 k - 4 k envs), per block when the chip is full (issue-bound: one warp runs the pass for the whole block,
-        // 3-5 % faster at 64 k - 1 M envs). Measured with scripts/gpu_ab_lp3.sh.
+        // 3-5 % faster at 64 k - 1 M envs). Measured with scripts/latency_probe.cu (-DCS_FLAT_WARP_LP3=0/1) and bench.py --lp3-queue.
         static int n_sm = 0;
         if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148; }
         const bool warpq = (g_lp3_queue < 0) ? (blocks * CS_FLAT_WPB <= 12 * n_sm) : (g_lp3_queue == 1);
