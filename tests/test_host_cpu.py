@@ -270,3 +270,40 @@ def test_om_sarl_policy_logic_matches_reference_on_oracle_backed_env(oracle):
         ref = np.array([float(v) for v in r['values']])
         assert np.abs(vals[e] - ref).max() < 1e-5, e
         assert [float(x) for x in r['action']] == [float(x) for x in act[e]], e
+
+
+def test_compat_agent_kinematics():
+    """crowdnav_b200.compat.agents.Agent: agent.py:47-138 semantics (set / accessors / holonomic and unicycle stepping /
+    goal test) on hand-computed values. (Bit-exact equivalence with the reference class on thousands of random steps was
+    checked in the dev container when the class was written; numpy's cos/sin are used like the reference does.)"""
+    from crowdnav_b200.batched import default_config
+    from crowdnav_b200.compat.agents import Agent, Robot
+    from crowdnav_b200.compat.statetypes import ActionXY, ActionRot
+    cfg = default_config()
+    a = Agent(cfg, 'humans')
+    assert (a.radius, a.v_pref, a.visible, a.sensor, a.kinematics) == (0.3, 1.0, True, 'coordinates', 'holonomic')
+    a.time_step = 0.25
+    a.set(1.0, 2.0, 5.0, 6.0, 0.1, 0.2, 0.5)
+    assert (a.get_position(), a.get_goal_position(), a.get_velocity()) == ((1.0, 2.0), (5.0, 6.0), (0.1, 0.2))
+    assert a.compute_position(ActionXY(1.0, -2.0), 0.25) == (1.25, 1.5)
+    nxt = a.get_next_observable_state(ActionXY(1.0, -2.0))
+    assert (nxt.px, nxt.py, nxt.vx, nxt.vy, nxt.radius) == (1.25, 1.5, 1.0, -2.0, 0.3)
+    a.step(ActionXY(1.0, -2.0))
+    assert (a.px, a.py, a.vx, a.vy, a.theta) == (1.25, 1.5, 1.0, -2.0, 0.5)
+    with pytest.raises(AssertionError):
+        a.step(ActionRot(1.0, 0.0))
+    a.set(1, 2, 1.1, 2.1, 0, 0, 0, radius=0.4, v_pref=1.3)
+    assert (a.radius, a.v_pref) == (0.4, 1.3) and a.reached_destination()
+    a.set(1, 2, 2, 3, 0, 0, 0)
+    assert not a.reached_destination()
+    a.set_position((3, 4)); a.set_velocity([5, 6])
+    assert (a.px, a.py, a.vx, a.vy) == (3, 4, 5, 6)
+    u = Agent(cfg, 'humans'); u.kinematics = 'unicycle'; u.time_step = 0.25
+    u.set(0.0, 0.0, 1.0, 1.0, 0.0, 0.0, np.pi / 2)
+    u.step(ActionRot(1.0, np.pi / 2))                       # turn left by 90 degrees, then 0.25 m along -x
+    assert abs(u.px + 0.25) < 1e-15 and abs(u.py) < 1e-15 and abs(u.theta - np.pi) < 1e-15
+    assert abs(u.vx + 1.0) < 1e-15 and abs(u.vy) < 1e-15
+    r = Robot(cfg, 'robot')
+    assert r.policy is None and r.visible is False
+    with pytest.raises(AttributeError):
+        r.act([])
