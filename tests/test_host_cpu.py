@@ -307,3 +307,92 @@ def test_compat_agent_kinematics():
     assert r.policy is None and r.visible is False
     with pytest.raises(AttributeError):
         r.act([])
+
+
+def test_compat_explorer_on_scripted_env():
+    """crowdnav_b200.compat.explorer.Explorer (explorer.py:21-125 surface) on a scripted environment: log lines equal
+    the shared reducer's on the same episodes, discounted returns / IL values / RL bootstraps follow the reference's
+    formulas (exponent (t * time_step) * v_pref), timeouts are not stored, bad end signals raise."""
+    import logging
+    from crowdnav_b200.compat.explorer import Explorer
+    from crowdnav_b200.compat.statetypes import Collision, Danger, Nothing, ReachGoal, Timeout
+    from crowdnav_b200.explorer import summarize
+
+    script = [  # per episode: list of (reward, info) ; the last step ends the episode
+        [(0.0, Nothing()), (-0.02, Danger(0.12)), (1.0, ReachGoal())],
+        [(-0.01, Danger(0.18)), (-0.25, Collision())],
+        [(0.0, Nothing())] * 3 + [(0.0, Timeout())],
+    ]
+
+    class Policy(object):
+        last_state = None
+
+        def set_phase(self, phase):
+            self.phase = phase
+
+        def transform(self, state):
+            return state * 2
+
+    class Robot(object):
+        time_step, v_pref = 0.25, 1.3
+        policy = Policy()
+
+        def act(self, ob):
+            self.policy.last_state = torch.tensor([float(ob)])
+            return ob
+
+    class Env(object):
+        time_limit = 25
+        global_time = 0.0
+
+        def __init__(self):
+            self.ep = -1
+
+        def reset(self, phase):
+            self.ep += 1; self.t = 0; self.global_time = 0.0
+            return 100 * self.ep
+
+        def step(self, action):
+            r, info = script[self.ep][self.t]
+            self.t += 1; self.global_time += 0.25
+            return 100 * self.ep + self.t, r, self.t == len(script[self.ep]), info
+
+    class Memory(list):
+        def push(self, item):
+            self.append(item)
+
+    lines = []
+    handler = logging.Handler(); handler.emit = lambda rec: lines.append(rec.getMessage())
+    root = logging.getLogger(); root.addHandler(handler); old = root.level; root.setLevel(logging.INFO)
+    mem = Memory()
+    robot = Robot()
+    ex = Explorer(Env(), robot, torch.device('cpu'), memory=mem, gamma=0.9, target_policy=robot.policy)
+    try:
+        ex.run_k_episodes(3, 'val', update_memory=True, imitation_learning=True, episode=7, print_failure=True)
+    finally:
+        root.removeHandler(handler); root.setLevel(old)
+    g = lambda t: pow(0.9, t * 0.25 * 1.3)  # noqa: E731
+    rets = [g(1) * -0.02 + g(2) * 1.0, -0.01 + g(1) * -0.25, 0.0]
+    rows = torch.tensor([[2, 3, 0.75, rets[0], 1, 0.12], [3, 2, 0.5, rets[1], 1, 0.18], [4, 4, 25, rets[2], 0, 0.0]], dtype=torch.float64)
+    expect = []
+    summarize(rows, 3, 'val', 25, 0.25, episode=7, print_failure=True, log=expect.append)
+    assert lines == expect and 'in episode 7' in lines[0] and lines[-1] == 'Timeout cases: 2'
+    # imitation learning: 3 + 2 pairs (the timeout episode is not stored), state transformed, value = return-to-go
+    assert len(mem) == 5
+    assert float(mem[0][0]) == 0.0 and float(mem[1][0]) == 2.0 and float(mem[3][0]) == 200.0
+    want = [rets[0], -0.02 + g(1) * 1.0, 1.0, rets[1], -0.25]
+    assert [float(v) for _, v in mem] == [float(torch.Tensor([w])) for w in want]
+    # RL targets: reward + gamma^(dt v_pref) * V_target(next state); terminal step: the reward
+    mem2 = Memory()
+    ex2 = Explorer(Env(), robot, torch.device('cpu'), memory=mem2, gamma=0.9)
+    ex2.update_target_model(torch.nn.Linear(1, 1))
+    with torch.no_grad():
+        ex2.target_model.weight.fill_(0.5); ex2.target_model.bias.fill_(0.25)
+    ex2.update_memory([torch.tensor([1.0]), torch.tensor([3.0])], None, [0.1, -0.25])
+    assert float(mem2[0][1]) == float(torch.Tensor([0.1 + pow(0.9, 0.25 * 1.3) * (0.5 * 3.0 + 0.25)])) and float(mem2[1][1]) == -0.25
+    with pytest.raises(ValueError):
+        Explorer(Env(), robot, torch.device('cpu')).update_memory([], None, [])
+    bad = Env(); script.append([(0.0, Nothing())])
+    bad.ep = 2
+    with pytest.raises(ValueError):
+        Explorer(bad, robot, torch.device('cpu'), gamma=0.9).run_k_episodes(1, 'test')
