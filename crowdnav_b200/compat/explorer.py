@@ -9,7 +9,7 @@ import copy
 import torch
 
 from .. import _abi
-from ..explorer import summarize
+from ..explorer import average, summarize  # noqa: F401  (average: module-level name of the reference explorer.py:128-132)
 from .statetypes import Collision, Danger, ReachGoal, Timeout
 
 _TERMINAL_CODE = {ReachGoal: _abi.INFO_REACHGOAL, Collision: _abi.INFO_COLLISION, Timeout: _abi.INFO_TIMEOUT}
