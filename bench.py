@@ -29,7 +29,11 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = 'env-steps/sec at 5 humans x batched envs'
+try:                                             # the metric string is BASELINE.json's, verbatim
+    with open(os.path.join(ROOT, 'BASELINE.json')) as _f:
+        METRIC = json.load(_f)['metric']
+except Exception:
+    METRIC = 'env-steps/sec at 5 humans x batched envs; 500-case success/collision parity'
 ALG_BYTES = lambda n: 8 * (19 + 12 * n) + 2      # 634 B at N=5, 2074 B at N=20  # noqa: E731
 
 
@@ -511,6 +515,23 @@ def run_ours(args):
         cpu = {'value': v, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
                'sample': sample + '; C restatement of the reference loop (oracle/crowdsim_oracle.c), OpenMP over envs'}
 
+    # ---- second half of the metric ("500-case success/collision parity"): BASELINE config 1's 500 test cases (seeds 1000..1499,
+    # ORCA robot) through BatchedExplorer on this GPU, against the reference's recorded outcome (tests/golden).
+    # Outside every timed region; a failure here is reported, it does not take the throughput line down.
+    parity = None
+    if rank == 0:
+        try:
+            from crowdnav_b200.explorer import BatchedExplorer
+            penv = BatchedCrowdSim(512, device=dev)
+            penv.configure(default_config(human_num=5))
+            st500 = BatchedExplorer(penv, 'orca', gamma=0.9).run_k_episodes(500, 'test')
+            ref500 = {'success': 213, 'collision': 284, 'timeout': 3, 'timeout_cases': [118, 168, 224], 'env_steps': 15190}
+            got500 = {k_: st500[k_] for k_ in ref500}
+            parity = {'cases': 500, 'ours': got500, 'reference': ref500, 'match': got500 == ref500,
+                      'note': 'test.py --policy orca flow (5 humans, circle_crossing, invisible robot); per-case bit-exact parity is in tests/'}
+        except Exception as ex:                              # noqa: BLE001
+            parity = {'error': repr(ex)}
+
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': K, 'warmup': max(W, 3),
                 'ms_per_step': ms_max / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -525,7 +546,7 @@ def run_ours(args):
                 'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                         'steps': ke, 'batches_in_flight': P, 'single_batch_blocking': e2e_single,
                         'note': 'HostStepper.launch()/wait() round-robin over %d independent 4096-env batches: per batch-step a pinned host action buffer goes up and obs/reward/done/info/next ORCA action come down (byte counts are per batch-step), the host waits for a batch\'s results before it feeds that batch again; single_batch_blocking = one batch, host blocks on every step' % P},
-                'single_stream': single, 'episodes': episodes, 'roofline': roofline, 'scale': scale, 'cpu_baseline': cpu}
+                'single_stream': single, 'parity_500_cases': parity, 'episodes': episodes, 'roofline': roofline, 'scale': scale, 'cpu_baseline': cpu}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
