@@ -14,6 +14,7 @@ What is recorded (floats as repr() strings, exact round trip):
   reset_*.json   initial scenes straight after env.reset (scenario generators + MT19937)
   rotate.json    CADRL.rotate + one-step lookahead inputs/outputs of MultiHumanRL.predict's inner loop
   occupancy_maps.json  MultiHumanRL.build_occupancy_maps on scene / lookahead / random human states
+  policy_decisions.json  per-action values and greedy actions of the reference's CADRL / LSTM-RL policies
 
 usage: python oracle/gen_golden.py [--quick]
 """
@@ -320,7 +321,47 @@ def run_om():
     print('occupancy map rows', len(rows))
 
 
+def run_policy_decisions():
+    """Greedy decisions of the reference's own CADRL and LSTM-RL policies (seed-0 weights, policy.config defaults, query_env):
+    per-action values reward + gamma^(dt v_pref) * V and the chosen action on scenes a few steps into test episodes."""
+    out = {}
+    for key, name, tweak in (('cadrl', 'cadrl', None), ('lstm_rl', 'lstm_rl', None),
+                             ('lstm_rl_interaction', 'lstm_rl', ('lstm_rl', 'with_interaction_module', 'true'))):
+        pcfg = configparser.RawConfigParser()
+        pcfg.read(os.path.join(REF, 'crowd_nav', 'configs', 'policy.config'))
+        if tweak:
+            pcfg.set(*tweak)
+        torch.manual_seed(0)
+        env, robot, _ = make_env(human_num=5, test_sim='circle_crossing', policy_name=name, policy_config=pcfg)
+        policy = robot.policy
+        decisions = []
+        for case in (0, 3, 7):
+            ob = env.reset('test', case)
+            orca_robot = ORCA()
+            orca_robot.time_step = env.time_step
+            for step in range(12):
+                state = JointState(robot.get_full_state(), ob)
+                if step % 4 == 0:
+                    np_state = np.random.get_state()
+                    chosen = policy.predict(JointState(robot.get_full_state(), list(ob)))
+                    np.random.set_state(np_state)
+                    decisions.append({'case': case, 'step': step, 'scene': scene(env), 'global_time': R(env.global_time),
+                                      'action': [R(chosen.vx), R(chosen.vy)], 'values': [R(v) for v in policy.action_values]})
+                action = orca_robot.predict(state)
+                ob, reward, done, info = env.step(ActionXY(action.vx, action.vy))
+                if done:
+                    break
+        out[key] = {'seed': 0, 'gamma': policy.gamma, 'decisions': decisions}
+        print(key, 'decisions', len(decisions))
+    with gzip.open(os.path.join(OUT, 'policy_decisions.json.gz'), 'wt') as f:
+        json.dump(out, f, separators=(',', ':'))
+
+
 def main():
+    if '--policies-only' in sys.argv:
+        os.makedirs(OUT, exist_ok=True)
+        run_policy_decisions()
+        return
     if '--mixed-only' in sys.argv:
         os.makedirs(OUT, exist_ok=True)
         run_mixed()
@@ -351,6 +392,7 @@ def main():
     run_resets()
     run_rotate()
     run_om()
+    run_policy_decisions()
 
 
 if __name__ == '__main__':

@@ -396,3 +396,50 @@ def test_compat_explorer_on_scripted_env():
     bad.ep = 2
     with pytest.raises(ValueError):
         Explorer(bad, robot, torch.device('cpu'), gamma=0.9).run_k_episodes(1, 'test')
+
+
+def _oracle_backed_env(oracle, rows):
+    """Stand-in for BatchedCrowdSim in CPU tests of the policy host logic: the kernels' outputs come from the oracle."""
+    from util import fill_host_state
+    host = fill_host_state(oracle, [r['scene'] for r in rows], 5)
+    host.g_time[:] = [float(r['global_time']) for r in rows]
+    prm = oracle.default_params(robot_policy=0)
+
+    class State(object):
+        r_pos, r_goal, r_attr = torch.from_numpy(host.r_pos), torch.from_numpy(host.r_goal), torch.from_numpy(host.r_attr)
+
+    class Env(object):
+        B, human_num, device, state = len(rows), 5, torch.device('cpu'), State()
+
+        def lookahead_pack(self, actions, out_states=None, out_reward=None):
+            s, r = oracle.lookahead_pack(prm, host, actions.numpy())
+            return torch.from_numpy(s), torch.from_numpy(r)
+
+        def lookahead_humans(self):
+            p, v = oracle.lookahead_humans(prm, host)
+            return torch.from_numpy(p), torch.from_numpy(v)
+
+        def occupancy_maps(self, p, v, cell_num, cell_size, channels):
+            return torch.from_numpy(oracle.occupancy_maps(p.numpy(), v.numpy(), cell_num, cell_size, channels))
+    return Env()
+
+
+@pytest.mark.parametrize('key', ['cadrl', 'lstm_rl', 'lstm_rl_interaction'])
+def test_cadrl_and_lstm_rl_policy_logic_matches_reference(oracle, key):
+    """BatchedValuePolicy for CADRL (min over the per-human values, cadrl.py:163-166) and LSTM-RL (with query_env the
+    lookahead rows reach the LSTM in env order) against the reference's own per-action values and greedy
+    actions (tests/golden/policy_decisions: seed-0 weights, policy.config defaults)."""
+    from crowdnav_b200.policy import make_cadrl, make_lstm_rl
+    d = load_golden('policy_decisions')[key]
+    rows = d['decisions']
+    pol = {'cadrl': lambda: make_cadrl(gamma=d['gamma'], seed=d['seed']),
+           'lstm_rl': lambda: make_lstm_rl(gamma=d['gamma'], seed=d['seed']),
+           'lstm_rl_interaction': lambda: make_lstm_rl(gamma=d['gamma'], seed=d['seed'], with_interaction_module=True)}[key]()
+    act = pol.act_batch(_oracle_backed_env(oracle, rows)).numpy()
+    vals = pol.action_values.numpy()
+    for e, r in enumerate(rows):
+        ref = np.array([float(v) for v in r['values']])
+        assert np.abs(vals[e] - ref).max() < 1e-5, (key, e, float(np.abs(vals[e] - ref).max()))
+        top2 = np.sort(ref)[-2:]
+        if top2[1] - top2[0] > 1e-4:
+            assert [float(x) for x in r['action']] == [float(x) for x in act[e]], (key, e)
