@@ -11,7 +11,6 @@ Mirrors the reference environment's surface for a batch (paths relative to /root
 There is no CPU fallback: without the CUDA library / a GPU these calls raise.
 """
 import ctypes as C
-import math
 
 import numpy as np
 import torch

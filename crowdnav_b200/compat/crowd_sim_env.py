@@ -14,10 +14,9 @@ import logging
 import numpy as np
 import torch
 
-from .. import _abi
 from ..batched import BatchedCrowdSim
 from .agents import Human
-from .statetypes import ActionRot, ActionXY, ObservableState, info_from_code
+from .statetypes import ActionRot, ObservableState, info_from_code
 
 
 class CrowdSim(object):

@@ -10,7 +10,6 @@ Module / parameter names of the networks equal the reference's (sarl.py:9-65, ca
 checkpoints (rl_model.pth / il_model.pth state_dicts) load unchanged with load_state_dict().
 """
 import itertools
-import math
 
 import numpy as np
 import torch

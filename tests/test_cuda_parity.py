@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from util import SUITES, load_golden, scene_arrays, fill_host_state, ulp_diff
+from util import SUITES, load_golden, scene_arrays, fill_host_state
 
 pytestmark = pytest.mark.gpu
 
