@@ -127,27 +127,27 @@ class ClockSampler(object):
 
 # ----------------------------------------------------------------------------------------------------------------------
 def pick_threads(po, args):
-    """'All the host threads it can use': OpenMP over envs scales until the per-pass work (a few ms) is eaten by
-    fork/join and SMT oversubscription, so calibrate: time a few passes at cpu_count, /2, /4, ... and keep the best."""
+    """'All the host threads it can use': each thread owns a fixed range of the batch's envs inside one parallel region
+    (oracle.run_passes); SMT oversubscription or a busy host can still make fewer threads faster, so calibrate: time short
+    runs at cpu_count, /2, /4, ... and keep the best."""
     import numpy as np
     B, N = args.envs, args.humans
     prm = po.default_params()
     st = po.HostState(B, N); io = po.HostStepIO(B)
     seeds = (np.arange(B) + 2000).astype(np.uint32)
-    po.reset(st, seeds, args.rule)
+    po.reset(st, seeds, args.rule, seed_stride=B)
     best = (0.0, 1)
     n = os.cpu_count() or 1
     cands = sorted({max(1, n >> s) for s in range(0, 6)}, reverse=True)
     for th in cands:
         po.set_threads(th)
-        for _ in range(3):
-            po.step(prm, st, io)
+        po.run_passes(prm, st, io, seeds, 10, args.rule, seed_stride=B)
         rate = 0.0
-        for _ in range(3):                               # best of 3 short trials per thread count
-            t0 = time.perf_counter()
-            for _ in range(10):
-                po.step(prm, st, io)
-            rate = max(rate, 10 * B / (time.perf_counter() - t0))
+        for _ in range(3):                               # best of 3 short trials (>= 60 ms each) per thread count
+            t0 = time.perf_counter(); done = 0
+            while time.perf_counter() - t0 < 0.06:
+                po.run_passes(prm, st, io, seeds, 20, args.rule, seed_stride=B); done += 20
+            rate = max(rate, done * B / (time.perf_counter() - t0))
         if rate > best[0]:
             best = (rate, th)
     po.set_threads(best[1])
@@ -166,20 +166,15 @@ def cpu_oracle_rate(args, seconds=12.0):
     st = po.HostState(B, N); io = po.HostStepIO(B)
     seeds = (np.arange(B) + 2000).astype(np.uint32)
     po.reset(st, seeds, args.rule, seed_stride=B)
-    for _ in range(3):
-        po.step(prm, st, io)
+    po.run_passes(prm, st, io, seeds, 50, args.rule, seed_stride=B)
     rates, n_total, t_begin = [], 0, time.perf_counter()
     for _ in range(5):                                   # median of 5 segments: the host is shared, single segments are noisy
         t0 = time.perf_counter(); n = 0
-        while True:
-            po.step(prm, st, io)
-            po.reset(st, seeds, args.rule, mask=io.done, seed_stride=B)
-            n += 1
-            if n % 8 == 0 and time.perf_counter() - t0 > seconds / 5:
-                break
+        while time.perf_counter() - t0 < seconds / 5:
+            po.run_passes(prm, st, io, seeds, 100, args.rule, seed_stride=B); n += 100
         rates.append(B * n / (time.perf_counter() - t0)); n_total += n
     rates.sort()
-    return rates[2], nthreads, '%d lockstep passes over a %d-env batch (auto-reset), %.1f s, median of 5 segments (min %.2e, max %.2e)' % (
+    return rates[2], nthreads, '%d lockstep passes over a %d-env batch (auto-reset) inside one OpenMP region, %.1f s, median of 5 segments (min %.2e, max %.2e)' % (
         n_total, B, time.perf_counter() - t_begin, rates[0], rates[-1])
 
 
@@ -202,16 +197,18 @@ def run_reference(args):
     seeds = (np.arange(B) + 2000).astype(np.uint32)
     po.reset(st, seeds, args.rule, seed_stride=B)
 
-    def one():
-        po.step(prm, st, io)
-        po.reset(st, seeds, args.rule, mask=io.done, seed_stride=B)
-    for _ in range(args.warmup):
-        one()
+    po.run_passes(prm, st, io, seeds, args.warmup, args.rule, seed_stride=B)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        one()
+    po.run_passes(prm, st, io, seeds, args.steps, args.rule, seed_stride=B)     # all passes inside one OpenMP parallel region
     dt = time.perf_counter() - t0
     v = B * args.steps / dt
+    # the same port driven one call per pass from the interpreter (step; reset of the finished envs), like a host loop would
+    t1 = time.perf_counter(); n_calls = 0
+    while time.perf_counter() - t1 < 1.0:
+        po.step(prm, st, io)
+        po.reset(st, seeds, args.rule, mask=io.done, seed_stride=B)
+        n_calls += 1
+    per_call = B * n_calls / (time.perf_counter() - t1)
     # context: the same path with the reference's STRUCTURE (interpreter-bound Python loop around a native rvo2 step,
     # oracle/pyloop.py) on a bounded sample -- the reference's real files cannot travel to this box
     py = None
@@ -229,8 +226,9 @@ def run_reference(args):
             'config': {'workload': WORKLOAD % (B, N, args.rule), 'envs_per_gpu': B, 'humans': N,
                        'note': 'CPU arm: one 4096-env batch stepped in lockstep by all host threads (rank 0 only)'},
             'cpu_baseline': {'value': v, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
-                             'sample': '%d lockstep passes over a %d-env batch per run; C restatement of the reference loop '
-                                       '(oracle/crowdsim_oracle.c, OpenMP over envs, thread count calibrated, host has %d logical CPUs)' % (args.steps, B, os.cpu_count() or 0)},
+                             'sample': '%d lockstep passes over a %d-env batch in one C call; C restatement of the reference loop '
+                                       '(oracle/crowdsim_oracle.c, OpenMP: every thread owns a range of envs, thread count calibrated, host has %d logical CPUs)' % (args.steps, B, os.cpu_count() or 0),
+                             'per_pass_calls_value': per_call},
             'e2e': {'value': v, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'python_loop': py, 'gpu_launches': 0}
     print(json.dumps(line))

@@ -225,25 +225,31 @@ static void generate_scene(mt_state *rngp, const crowdsim_reset_args *a, int N, 
     *rngp = rng;
 }
 
+/* crowd_sim.py:251-312 for ONE env slot: next seed, robot placement (:274), scene generation, bookkeeping reset. */
+static void reset_one(const crowdsim_reset_args *args, int e, int N, crowdsim_state *st, crowdsim_episodes *ep)
+{
+    uint32_t seed; int case_id;
+    if (!next_seed(args, e, &seed, &case_id)) { if (st->active) st->active[e] = 0; if (ep) ep->ep_case[e] = -1; return; }
+    mt_state rng; mt_seed(&rng, seed);
+    /* crowd_sim.py:274 robot.set(0, -R, 0, R, 0, 0, pi/2) */
+    st->r_pos[2 * e] = 0.0; st->r_pos[2 * e + 1] = -args->circle_radius; st->r_goal[2 * e] = 0.0; st->r_goal[2 * e + 1] = args->circle_radius;
+    st->r_vel[2 * e] = 0.0; st->r_vel[2 * e + 1] = 0.0;
+    st->r_attr[2 * e] = args->robot_radius; st->r_attr[2 * e + 1] = args->robot_v_pref;
+    st->r_theta[e] = PI_D / 2; st->g_time[e] = 0.0;
+    generate_scene(&rng, args, N, st->h_pos + (size_t)e * N * 2, st->h_goal + (size_t)e * N * 2, st->h_attr + (size_t)e * N * 2);
+    for (int i = 0; i < 2 * N; ++i) st->h_vel[(size_t)e * N * 2 + i] = 0.0;
+    if (st->active) st->active[e] = 1;
+    if (ep) { ep->ep_steps[e] = 0; ep->ep_return[e] = 0.0; ep->ep_too_close[e] = 0; ep->ep_min_dist_sum[e] = 0.0;
+              if (args->case_counter) ep->ep_case[e] = case_id; }
+}
+
 int oracle_crowdsim_reset(const crowdsim_reset_args *args, int B, int N, crowdsim_state *st, crowdsim_episodes *ep)
 {
     if (!args || !st || (!args->seed && !args->case_counter) || B < 0 || N < 0) return CROWDSIM_EINVAL;
     #pragma omp parallel for schedule(static)
     for (int e = 0; e < B; ++e) {
         if (args->mask && !args->mask[e]) continue;
-        uint32_t seed; int case_id;
-        if (!next_seed(args, e, &seed, &case_id)) { if (st->active) st->active[e] = 0; if (ep) ep->ep_case[e] = -1; continue; }
-        mt_state rng; mt_seed(&rng, seed);
-        /* crowd_sim.py:274 robot.set(0, -R, 0, R, 0, 0, pi/2) */
-        st->r_pos[2 * e] = 0.0; st->r_pos[2 * e + 1] = -args->circle_radius; st->r_goal[2 * e] = 0.0; st->r_goal[2 * e + 1] = args->circle_radius;
-        st->r_vel[2 * e] = 0.0; st->r_vel[2 * e + 1] = 0.0;
-        st->r_attr[2 * e] = args->robot_radius; st->r_attr[2 * e + 1] = args->robot_v_pref;
-        st->r_theta[e] = PI_D / 2; st->g_time[e] = 0.0;
-        generate_scene(&rng, args, N, st->h_pos + (size_t)e * N * 2, st->h_goal + (size_t)e * N * 2, st->h_attr + (size_t)e * N * 2);
-        for (int i = 0; i < 2 * N; ++i) st->h_vel[(size_t)e * N * 2 + i] = 0.0;
-        if (st->active) st->active[e] = 1;
-        if (ep) { ep->ep_steps[e] = 0; ep->ep_return[e] = 0.0; ep->ep_too_close[e] = 0; ep->ep_min_dist_sum[e] = 0.0;
-                  if (args->case_counter) ep->ep_case[e] = case_id; }
+        reset_one(args, e, N, st, ep);
     }
     return 0;
 }
@@ -420,6 +426,35 @@ int oracle_crowdsim_step(const crowdsim_params *prm, int B, int N, crowdsim_stat
         orc_stats stats = {0, 0, 0, 0};
         step_one(prm, e, N, st, io, ep, ar, &stats);
         s0 += stats.solves; s1 += stats.lines; s2 += stats.lp1_calls; s3 += stats.lp3_calls;
+    }
+    g_stats[0] += s0; g_stats[1] += s1; g_stats[2] += s2; g_stats[3] += s3;
+    return 0;
+}
+
+/* n_passes lockstep passes over the batch inside ONE parallel region (bench.py's CPU arm): every pass steps all envs and
+ * immediately re-generates the scene of each env whose episode ended (per-slot seed, advanced by seed_stride) -- the same
+ * result as n_passes x (oracle_crowdsim_step; oracle_crowdsim_reset(mask = done)), without the per-call interpreter and
+ * fork/join cost. Each thread owns a fixed range of envs; a barrier per pass keeps the passes in lockstep. */
+int oracle_crowdsim_run_passes(const crowdsim_params *prm, int B, int N, crowdsim_state *st, crowdsim_step_io *io,
+                               const crowdsim_reset_args *reset_args, int n_passes)
+{
+    if (!prm || !st || !io || !reset_args || !reset_args->seed || B < 0 || N < 0 || n_passes < 0) return CROWDSIM_EINVAL;
+    if (N > CROWDSIM_MAX_HUMANS || prm->max_neighbors > CROWDSIM_MAX_NEIGHBORS) return CROWDSIM_EUNSUPPORTED;
+    long s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    #pragma omp parallel reduction(+:s0,s1,s2,s3)
+    {
+        const int nt = omp_get_num_threads(), id = omp_get_thread_num();
+        const int lo = (int)((long long)B * id / nt), hi = (int)((long long)B * (id + 1) / nt);
+        for (int pass = 0; pass < n_passes; ++pass) {
+            for (int e = lo; e < hi; ++e) {
+                if (st->active && !st->active[e]) continue;
+                orc_stats stats = {0, 0, 0, 0};
+                step_one(prm, e, N, st, io, NULL, NULL, &stats);
+                s0 += stats.solves; s1 += stats.lines; s2 += stats.lp1_calls; s3 += stats.lp3_calls;
+                if (io->done[e]) reset_one(reset_args, e, N, st, NULL);
+            }
+            #pragma omp barrier
+        }
     }
     g_stats[0] += s0; g_stats[1] += s1; g_stats[2] += s2; g_stats[3] += s3;
     return 0;

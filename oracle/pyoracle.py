@@ -31,6 +31,9 @@ def lib():
         _abi.declare(l, prefix='oracle_crowdsim_', with_stream=False)
         l.oracle_mt19937_doubles.argtypes = [C.c_uint32, C.c_int, C.c_void_p]
         l.oracle_get_stats.argtypes = [C.c_void_p]
+        l.oracle_crowdsim_run_passes.restype = C.c_int
+        l.oracle_crowdsim_run_passes.argtypes = [C.POINTER(_abi.Params), C.c_int, C.c_int, C.POINTER(_abi.State),
+                                                 C.POINTER(_abi.StepIO), C.POINTER(_abi.ResetArgs), C.c_int]
         _lib = l
     return _lib
 
@@ -170,6 +173,19 @@ def step(prm, st, io, ep=None, ar=None):
     rc = lib().oracle_crowdsim_step(C.byref(prm), st.B, st.N, C.byref(s), C.byref(i),
                                     C.byref(e) if e is not None else None, C.byref(a) if a is not None else None)
     assert rc == 0, rc
+
+
+def run_passes(prm, st, io, seeds, n_passes, rule='circle_crossing', seed_stride=0, circle_radius=4.0, square_width=10.0,
+               human_radius=0.3, human_v_pref=1.0, robot_radius=0.3, robot_v_pref=1.0, discomfort_dist=0.2,
+               randomize_attributes=False):
+    """n_passes x (step; reset of the envs whose episode ended, from the per-slot seeds) inside one C call / one OpenMP
+    parallel region. `seeds` (uint32 [B]) is advanced in place by seed_stride per use, like reset(..., seed_stride=...)."""
+    assert isinstance(seeds, np.ndarray) and seeds.dtype == np.uint32 and seeds.flags['C_CONTIGUOUS']
+    a = _reset_args(seeds, rule, None, circle_radius, square_width, human_radius, human_v_pref, robot_radius,
+                    robot_v_pref, discomfort_dist, randomize_attributes, seed_stride, None, 0, 0)
+    s, i = st.struct(), io.struct()
+    rc = lib().oracle_crowdsim_run_passes(C.byref(prm), st.B, st.N, C.byref(s), C.byref(i), C.byref(a), int(n_passes))
+    _abi.check(rc, 'oracle_crowdsim_run_passes')
 
 
 def orca_act(prm, st):

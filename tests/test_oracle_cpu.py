@@ -266,3 +266,31 @@ def test_occupancy_maps_match_reference(oracle):
         assert np.array_equal(got != 0, ref != 0), r['tag']
         assert np.abs(got - ref).max() <= 1e-6, r['tag']
     assert any(np.array(r['maps'], dtype=np.float64).any() for r in rows)
+
+
+def test_run_passes_equals_step_plus_reset(oracle):
+    """oracle.run_passes (bench.py's CPU arm: n lockstep passes inside one OpenMP region, finished envs re-generated from
+    their per-slot seeds) is bit-identical to n x (step; reset(mask = done)), for any thread count."""
+    B, N, n = 300, 5, 60
+    prm = oracle.default_params()
+    def fresh():
+        st = oracle.HostState(B, N); io = oracle.HostStepIO(B)
+        seeds = (np.arange(B) + 2000).astype(np.uint32)
+        oracle.reset(st, seeds, 'circle_crossing', seed_stride=B)
+        return st, io, seeds
+    a_st, a_io, a_seeds = fresh()
+    finished = 0
+    for _ in range(n):
+        oracle.step(prm, a_st, a_io)
+        finished += int(a_io.done.sum())
+        oracle.reset(a_st, a_seeds, 'circle_crossing', mask=a_io.done, seed_stride=B)
+    assert finished > B                                      # every env finished at least one episode on average
+    for threads in (1, 3):
+        oracle.set_threads(threads)
+        b_st, b_io, b_seeds = fresh()
+        oracle.run_passes(prm, b_st, b_io, b_seeds, n // 2, 'circle_crossing', seed_stride=B)
+        oracle.run_passes(prm, b_st, b_io, b_seeds, n - n // 2, 'circle_crossing', seed_stride=B)
+        for f in ('h_pos', 'h_vel', 'h_goal', 'r_pos', 'r_vel', 'g_time'):
+            assert np.array_equal(getattr(a_st, f), getattr(b_st, f)), (threads, f)
+        assert np.array_equal(a_seeds, b_seeds) and np.array_equal(a_io.info, b_io.info) and np.array_equal(a_io.reward, b_io.reward)
+    oracle.set_threads(os.cpu_count() or 1)
