@@ -148,6 +148,8 @@ def pick_threads(po, args):
             while time.perf_counter() - t0 < 0.06:
                 po.run_passes(prm, st, io, seeds, 20, args.rule, seed_stride=B); done += 20
             rate = max(rate, done * B / (time.perf_counter() - t0))
+            if rate < 0.25 * best[0]:                    # hopeless thread count (oversubscribed / spinning): do not retry it
+                break
         if rate > best[0]:
             best = (rate, th)
     po.set_threads(best[1])
