@@ -5,6 +5,7 @@
 //   B  sequential lp2 + lp3 (shared-memory-column code path of the generic kernel, n <= 10)   vs  orc_lp2 / orc_lp3
 //   C  speculative lp1_all + lp2_scan (register path of the small-crowd kernel, n <= 5)        vs  orc_lp2
 //   D  lp3 as independent per-line sub-problems + lp3_outer_scan (the lane-parallel pass)      vs  orc_lp3
+//   E  neighbour_order (pair-wise ranks + packed indices of the small-crowd kernel)            vs  orc_insert_neighbor
 // Build (tests/test_native_cpu.py): nvcc -O2 --fmad=false -Xcompiler -ffp-contract=off -std=c++17 lp_fuzz.cu
 // Usage: lp_fuzz <cases> <seed>; prints coverage counters; exit code 0 iff every comparison was bit-identical.
 #include <cstdio>
@@ -59,6 +60,34 @@ static bool check_case(int n, const orc_line *ol, float radius, orc_v2 opt, long
     return true;
 }
 
+// ---- E: M candidates in scan order, some out of range, many exact ties: order and count must equal RVO2's insertion sort
+// (neighbour range 10 m, capacity max_nb >= M as in the small-crowd kernel's callers; truncation to max_nb < M keeps the
+// first max_nb entries of the same order) ----
+template <int M>
+static bool check_order(long *cov)
+{
+    float dsq[M]; bool inr[M]; int id[M], src[M];
+    const float range_sq = 100.0f;
+    const bool ties = rnd() % 3 == 0;
+    for (int c = 0; c < M; ++c) {
+        const float x = ties ? (float)(rnd() % 4) * 0.5f : uni(-9.f, 9.f), y = ties ? (float)(rnd() % 3) : uni(-9.f, 9.f);
+        dsq[c] = x * x + y * y;
+        const bool visible = (rnd() % 8) != 0;                 // e.g. the invisible robot's slot
+        inr[c] = visible && dsq[c] < range_sq;
+        id[c] = (c + (int)(rnd() % 2)) % 6;                    // agent indices < 8, not necessarily ascending
+    }
+    const int nl = orca::neighbour_order<M>(dsq, inr, id, src);
+    float nd[M]; int ni[M]; int cnt = 0; float rs = range_sq;
+    for (int c = 0; c < M; ++c) if (inr[c]) orc_insert_neighbor(dsq[c], id[c], nd, ni, &cnt, M, &rs);
+    if (nl != cnt) { printf("E count mismatch %d vs %d\n", nl, cnt); return false; }
+    for (int kk = 0; kk < M; ++kk) {
+        const int want = kk < cnt ? ni[kk] : 0;
+        if (src[kk] != want) { printf("E order mismatch at %d: %d vs %d (M=%d)\n", kk, src[kk], want, M); return false; }
+    }
+    cov[4] += 1; cov[5] += ties;
+    return true;
+}
+
 int main(int argc, char **argv)
 {
     const long cases = argc > 1 ? atol(argv[1]) : 200000;
@@ -99,7 +128,8 @@ int main(int argc, char **argv)
             }
         }
         if (!check_case<5>(n, ol, radius, opt, cov)) { printf("case %ld kind %d\n", c, kind); return 1; }
+        if (!(check_order<5>(cov) && check_order<4>(cov) && check_order<2>(cov) && check_order<1>(cov))) { printf("case %ld\n", c); return 1; }
     }
-    printf("ok cases=%ld lp3_needed=%ld speculative_checked=%ld overlapping_pairs=%ld forced_parallel_lines=%ld\n", cases, cov[0], cov[1], cov[2], cov[3]);
+    printf("ok cases=%ld lp3_needed=%ld speculative_checked=%ld overlapping_pairs=%ld forced_parallel_lines=%ld neighbour_orders=%ld neighbour_ties=%ld\n", cases, cov[0], cov[1], cov[2], cov[3], cov[4], cov[5]);
     return 0;
 }
