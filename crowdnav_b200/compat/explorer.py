@@ -41,10 +41,12 @@ class Explorer(object):
 
     def run_k_episodes(self, k, phase, update_memory=False, imitation_learning=False, episode=None, print_failure=False):
         self.robot.policy.set_phase(phase)
-        dt, v_pref = self.robot.time_step, self.robot.v_pref    # exponent = (t * dt) * v_pref, in the reference's association
         rows = []
         for _ in range(k):
             info, states, rewards, n_danger, danger_sum = self._rollout(phase)
+            # read AFTER the rollout: env.reset() is what assigns robot.time_step (crowd_sim.py:296-298; the reference
+            # reads it at explorer.py:71-72). exponent = (t * dt) * v_pref, in the reference's association
+            dt, v_pref = self.robot.time_step, self.robot.v_pref
             code = _TERMINAL_CODE.get(type(info))
             if code is None:
                 raise ValueError('Invalid end signal from environment')

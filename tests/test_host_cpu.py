@@ -236,7 +236,7 @@ def test_om_sarl_policy_logic_matches_reference_on_oracle_backed_env(oracle):
     """Host logic of BatchedValuePolicy with with_om (lookahead rows ++ occupancy maps of the next human states, broadcast
     over the 81 actions, value = reward + gamma^(dt v_pref) V) against the reference's own OM-SARL per-action values and
     greedy actions (tests/golden/occupancy_maps: om_sarl, seed-0 weights). The env is an oracle-backed stand-in here
-    (CPU test); tests/test_cuda_rollout.py runs the same check on the CUDA path."""
+    (CPU test); tests/test_cuda_1_rollout.py runs the same check on the CUDA path."""
     from util import fill_host_state
     from crowdnav_b200.policy import make_sarl
     o = load_golden('occupancy_maps')['om_sarl']
@@ -333,10 +333,12 @@ def test_compat_explorer_on_scripted_env():
         def transform(self, state):
             return state * 2
 
-    class Robot(object):
-        time_step, v_pref = 0.25, 1.3
-        policy = Policy()
+    from crowdnav_b200.batched import default_config
+    from crowdnav_b200.compat.agents import Robot as CompatRobot
 
+    class Robot(CompatRobot):
+        # the REAL compat Robot: time_step is None until env.reset() assigns it (agent.py:36, crowd_sim.py:296-298) -- a
+        # fake with a class-level time_step once hid a read-before-reset bug in run_k_episodes from the CPU suite
         def act(self, ob):
             self.policy.last_state = torch.tensor([float(ob)])
             return ob
@@ -345,11 +347,13 @@ def test_compat_explorer_on_scripted_env():
         time_limit = 25
         global_time = 0.0
 
-        def __init__(self):
-            self.ep = -1
+        def __init__(self, robot=None):
+            self.ep = -1; self.robot = robot
 
         def reset(self, phase):
             self.ep += 1; self.t = 0; self.global_time = 0.0
+            if self.robot is not None:
+                self.robot.time_step = 0.25               # like CrowdSim.reset (crowd_sim.py:296-298)
             return 100 * self.ep
 
         def step(self, action):
@@ -365,8 +369,9 @@ def test_compat_explorer_on_scripted_env():
     handler = logging.Handler(); handler.emit = lambda rec: lines.append(rec.getMessage())
     root = logging.getLogger(); root.addHandler(handler); old = root.level; root.setLevel(logging.INFO)
     mem = Memory()
-    robot = Robot()
-    ex = Explorer(Env(), robot, torch.device('cpu'), memory=mem, gamma=0.9, target_policy=robot.policy)
+    robot = Robot(default_config(), 'robot'); robot.policy = Policy(); robot.v_pref = 1.3
+    assert robot.time_step is None
+    ex = Explorer(Env(robot), robot, torch.device('cpu'), memory=mem, gamma=0.9, target_policy=robot.policy)
     try:
         ex.run_k_episodes(3, 'val', update_memory=True, imitation_learning=True, episode=7, print_failure=True)
     finally:
