@@ -48,7 +48,6 @@ def parse():
     ap.add_argument('--pools', type=int, default=0, help='independent batches rotated through (0 = enough to exceed L2)')
     ap.add_argument('--rule', default='circle_crossing')
     ap.add_argument('--streams', type=int, default=16, help='independent env batches stepped concurrently (CUDA streams inside the timed graph)')
-    ap.add_argument('--lp3-queue', default='auto', choices=['auto', 'block', 'warp'], help='tuning hook of the small-crowd step kernel (auto = by grid size)')
     ap.add_argument('--prefetch-every', type=int, default=4, help='scene-prefetch launch for a batch on every n-th visit of that batch')
     ap.add_argument('--e2e-batches', type=int, default=16, help='independent env batches kept in flight by the e2e leg')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -252,7 +251,6 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=dev)
     sampler = ClockSampler(local)                            # started early: its start-up must be over before the timed region
     lib = _abi.load()
-    lib.crowdsim_debug_lp3_queue({'auto': -1, 'block': 0, 'warp': 1}[args.lp3_queue])
     B, N, K, W = args.envs, args.humans, args.steps, args.warmup
     bytes_per_env = ALG_BYTES(N)
     pools = args.pools or max(2, int(1.3 * 126e6 / (B * bytes_per_env)) + 1)

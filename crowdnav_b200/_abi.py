@@ -7,7 +7,7 @@ for its CPU library. No torch types cross the boundary.
 import ctypes as C
 import os
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_HUMANS = 63
 MAX_NEIGHBORS = 10
 
@@ -73,6 +73,9 @@ def declare(lib, prefix='crowdsim_', with_stream=True):
     P = C.POINTER
     f = getattr(lib, prefix + 'step')
     f.restype, f.argtypes = C.c_int, [P(Params), C.c_int, C.c_int, P(State), P(StepIO), P(Episodes), P(AutoReset)] + s
+    if hasattr(lib, prefix + 'step_n'):
+        f = getattr(lib, prefix + 'step_n')
+        f.restype, f.argtypes = C.c_int, [P(Params), C.c_int, C.c_int, P(State), P(StepIO), P(Episodes), P(AutoReset), C.c_int] + s
     f = getattr(lib, prefix + 'prefetch_scenes')
     f.restype, f.argtypes = C.c_int, [P(ResetArgs), C.c_int, C.c_int, P(AutoReset)] + s
     f = getattr(lib, prefix + 'orca_act')
@@ -87,8 +90,8 @@ def declare(lib, prefix='crowdsim_', with_stream=True):
     return lib
 
 
-EXPORTS = ('crowdsim_abi_version', 'crowdsim_device_check', 'crowdsim_launch_count', 'crowdsim_debug_force_generic', 'crowdsim_debug_lp3_queue', 'crowdsim_graph_launch',
-           'crowdsim_event_wait', 'crowdsim_step',
+EXPORTS = ('crowdsim_abi_version', 'crowdsim_device_check', 'crowdsim_launch_count', 'crowdsim_debug_force_generic', 'crowdsim_graph_launch',
+           'crowdsim_event_wait', 'crowdsim_step', 'crowdsim_step_n',
            'crowdsim_orca_act', 'crowdsim_reset', 'crowdsim_prefetch_scenes', 'crowdsim_pack_joint', 'crowdsim_lookahead_pack',
            'crowdsim_lookahead_humans', 'crowdsim_occupancy_maps')
 
@@ -118,8 +121,6 @@ def load():
         lib.crowdsim_launch_count.restype = C.c_ulonglong
         lib.crowdsim_debug_force_generic.argtypes = [C.c_int]
         lib.crowdsim_debug_force_generic.restype = None
-        lib.crowdsim_debug_lp3_queue.argtypes = [C.c_int]
-        lib.crowdsim_debug_lp3_queue.restype = None
         lib.crowdsim_graph_launch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.crowdsim_graph_launch.restype = C.c_int
         lib.crowdsim_event_wait.argtypes = [C.c_void_p]

@@ -289,8 +289,11 @@ class BatchedCrowdSim(object):
         _abi.check(rc, 'crowdsim_prefetch_scenes')
 
     # ---- step ----------------------------------------------------------------------------------------------------
-    def step(self, actions=None):
-        """One lockstep env-step. `actions` [B][2] float64 device tensor (vx,vy) / (v,r); None when the robot runs ORCA."""
+    def step(self, actions=None, n_steps=1):
+        """One lockstep env-step. `actions` [B][2] float64 device tensor (vx,vy) / (v,r); None when the robot runs ORCA.
+        n_steps > 1: crowdsim_step_n -- exactly n_steps single steps; with an ORCA robot and N <= 5 they run inside ONE
+        kernel launch with the state in registers (the closed episode loop of explorer.py:41-43). The returned reward /
+        done / info are those of each env's last live step."""
         if self.robot_policy != _abi.ROBOT_ORCA:
             if actions is None:
                 raise ValueError('robot policy is external: actions required')
@@ -302,11 +305,20 @@ class BatchedCrowdSim(object):
                          _ptr(self.done), _ptr(self.info))
         ep = self.episodes.struct() if self.episodes is not None else None
         ar = self.autoreset.struct() if self.autoreset is not None else None
-        rc = self.lib.crowdsim_step(C.byref(prm), self.B, self.human_num, C.byref(st), C.byref(io),
-                                    C.byref(ep) if ep is not None else None, C.byref(ar) if ar is not None else None,
-                                    self._stream())
+        if n_steps == 1:
+            rc = self.lib.crowdsim_step(C.byref(prm), self.B, self.human_num, C.byref(st), C.byref(io),
+                                        C.byref(ep) if ep is not None else None, C.byref(ar) if ar is not None else None,
+                                        self._stream())
+        else:
+            rc = self.lib.crowdsim_step_n(C.byref(prm), self.B, self.human_num, C.byref(st), C.byref(io),
+                                          C.byref(ep) if ep is not None else None, C.byref(ar) if ar is not None else None,
+                                          int(n_steps), self._stream())
         _abi.check(rc, 'crowdsim_step')
         return self.observation(), self.reward, self.done, self.info
+
+    def step_n(self, n_steps):
+        """n_steps closed-loop env-steps (ORCA robot): see step()."""
+        return self.step(None, n_steps=n_steps)
 
     def orca_act(self, out=None):
         out = self.action_out if out is None else out

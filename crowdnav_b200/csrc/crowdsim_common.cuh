@@ -29,6 +29,16 @@ __device__ __forceinline__ double point_to_segment_dist0(double x1, double y1, d
 
 __device__ __forceinline__ double2 ld2(const double *p, size_t i) { return reinterpret_cast<const double2 *>(p)[i]; }
 __device__ __forceinline__ void st2(double *p, size_t i, double2 v) { reinterpret_cast<double2 *>(p)[i] = v; }
+__device__ __forceinline__ double2 ld2_cg(const double *p, size_t i) { return __ldcg(reinterpret_cast<const double2 *>(p) + i); }
+
+// Slot flags of the auto-reset protocol (include/crowdsim_b200.h: crowdsim_autoreset). The generator and the step kernels may
+// run concurrently on different streams, so the hand-over is a formal release / acquire pair at gpu scope:
+//   generator:  ld.acquire(flag) == EMPTY  ->  write the scene  ->  st.release(flag, READY)
+//   consumer:   ld.relaxed(flag) == READY decides; every lane that reads slot data does ld.acquire(flag) first;
+//               after the lanes re-converged, st.release(flag, EMPTY)
+__device__ __forceinline__ uint8_t ld_relaxed_u8(const uint8_t *p) { unsigned v; asm volatile("ld.relaxed.gpu.global.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return (uint8_t)v; }
+__device__ __forceinline__ uint8_t ld_acquire_u8(const uint8_t *p) { unsigned v; asm volatile("ld.acquire.gpu.global.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return (uint8_t)v; }
+__device__ __forceinline__ void st_release_u8(uint8_t *p, uint8_t v) { asm volatile("st.release.gpu.global.u8 [%0], %1;" :: "l"(p), "r"((unsigned)v) : "memory"); }
 
 // Device-side copy of the scalar parameters (passed by value as a kernel argument).
 struct KParams {

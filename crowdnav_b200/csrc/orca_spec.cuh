@@ -167,4 +167,46 @@ ORCA_HD __forceinline__ V2 lp2_init(V2 opt, float radius)
     return opt;
 }
 
+// ---- linearProgram3 spread over lanes (step_flat.cuh, step_mid.cuh) ----------------------------------------------------
+// RVO2's linearProgram3 visits the lines i = begin .. n-1; for a line that is violated by more than the running `distance`
+// it builds the lines j < i projected onto i and solves linearProgram2 over them in direction-optimisation mode, STARTING
+// FROM optVelocity * radius -- so the sub-problem of line i depends only on the lines, never on the running result.
+// That gives three levels of independent work per solve: the (i, j) projections (one division + one normalisation each),
+// the per-i sub-problems (speculative lp1_all + lp2_scan over <= M-1 projected lines, all pair intersections in flight at
+// once), and a short outer scan. The kernels put each level on its own set of lanes; these are the per-lane functions
+// (host-compilable: tests/native/lp_fuzz.cu part F checks the composition against the oracle's sequential lp3).
+
+// pair index q = i (i - 1) / 2 + j  <->  (i, j), 0 <= j < i <= 9
+ORCA_HD __forceinline__ void lp3_pair_of(int q, int &i, int &j)
+{
+    i = 1 + (q >= 1) + (q >= 3) + (q >= 6) + (q >= 10) + (q >= 15) + (q >= 21) + (q >= 28) + (q >= 36);
+    j = q - i * (i - 1) / 2;
+}
+
+// Line j projected onto line i (the loop body of linearProgram3, same operations as lp3_project). Returns false for the
+// pairs RVO2 skips (parallel, same direction). Parallel lanes divide 1 by 1 (the quotient is unused there): a zero
+// denominator would send the whole warp through the IEEE-division slow path.
+ORCA_HD __forceinline__ bool lp3_project_pair(V2 pi, V2 di, V2 pj, V2 dj, V2 &pp, V2 &pd)
+{
+    const float d = det(di, dj);
+    const bool par = fabsf(d) <= kEps;
+    if (par && dot(di, dj) > 0.0f) { pp = mk(0.f, 0.f); pd = mk(0.f, 0.f); return false; }
+    const float t = (par ? 1.0f : det(dj, pi - pj)) / (par ? 1.0f : d);
+    pp = par ? 0.5f * (pi + pj) : pi + t * di;
+    pd = normalize(dj - di);
+    return true;
+}
+
+// Sub-problem of line i: linearProgram2 (direction optimisation, opt = perpendicular of dir_i) over its K projected-line
+// positions (absent / skipped positions: valid = false, zero lines). Returns false when it fails (RVO2 keeps the running
+// result then); r2 = the point it returns.
+template <int K>
+ORCA_HD __forceinline__ bool lp3_sub_spec(const RegLines<K> &P, const bool (&valid)[K], float radius, V2 di, V2 &r2)
+{
+    const V2 opt = mk(-di.y, di.x);
+    V2 cand[K]; bool feas[K];
+    lp1_all<K, K>(P, valid, radius, opt, true, cand, feas);
+    return lp2_scan<K, K>(P, valid, K, cand, feas, mk(opt.x * radius, opt.y * radius), r2) == K;
+}
+
 }  // namespace orca

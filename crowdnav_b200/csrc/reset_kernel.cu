@@ -223,12 +223,11 @@ __device__ __forceinline__ void prefetch_env(const ResetKArgs &A, int e, MT &rng
     const crowdsim_autoreset &ar = A.ar;
     const int N = A.N;
     uint32_t seed; int case_id;
-    if (!next_seed(A.a, e, seed, case_id)) { ar.n_state[e] = CROWDSIM_SLOT_EXHAUSTED; return; }
+    if (!next_seed(A.a, e, seed, case_id)) { st_release_u8(ar.n_state + e, CROWDSIM_SLOT_EXHAUSTED); return; }
     rng.seed(seed);
     generate_scene(rng, A.a, N, ar.n_h_pos + (size_t)e * N * 2, ar.n_h_goal + (size_t)e * N * 2, ar.n_h_attr + (size_t)e * N * 2);
     ar.n_case[e] = case_id;
-    __threadfence();                                       // scene visible before the flag
-    *reinterpret_cast<volatile uint8_t *>(ar.n_state + e) = CROWDSIM_SLOT_READY;
+    st_release_u8(ar.n_state + e, CROWDSIM_SLOT_READY);    // scene visible before the flag (release at gpu scope)
 }
 
 template <bool PREFETCH>
@@ -240,7 +239,9 @@ __global__ void __launch_bounds__(kSlotsPerBlock) scene_kernel(const __grid_cons
     const int e = blockIdx.x * kSlotsPerBlock + threadIdx.x;
     bool need = e < A.B;
     if (need) {
-        if (PREFETCH) need = *reinterpret_cast<volatile uint8_t *>(A.ar.n_state + e) == CROWDSIM_SLOT_EMPTY;
+        // acquire: the consumer's reads of the previous scene happen-before the writes of the next one (the generating
+        // thread is ordered behind this one by the block barrier of compact_block)
+        if (PREFETCH) need = ld_acquire_u8(A.ar.n_state + e) == CROWDSIM_SLOT_EMPTY;
         else need = !(A.a.mask && !A.a.mask[e]);
     }
     const int count = compact_block(need, e, s_list, &s_count);
@@ -256,11 +257,13 @@ template <bool PREFETCH>
 static int launch_scene_kernel(const ResetKArgs &A, int B, cudaStream_t stream)
 {
     const size_t smem = (size_t)624 * kGen * sizeof(uint32_t);
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[PREFETCH]) {
+    static bool attr_set_dev[2][64];                       // the attribute is per DEVICE: cache keyed by the current device
+    int dev = 0; cudaGetDevice(&dev);
+    bool dummy = false; bool &attr_done = (dev >= 0 && dev < 64) ? attr_set_dev[PREFETCH][dev] : dummy;
+    if (!attr_done) {
         cudaError_t err = cudaFuncSetAttribute(scene_kernel<PREFETCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return (int)err;
-        attr_set[PREFETCH] = true;
+        attr_done = true;
     }
     const int blocks = (B + kSlotsPerBlock - 1) / kSlotsPerBlock;
     scene_kernel<PREFETCH><<<blocks, kSlotsPerBlock, smem, stream>>>(A);

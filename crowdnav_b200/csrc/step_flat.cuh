@@ -1,4 +1,4 @@
-// step_flat.cuh -- CrowdSim step for small crowds (N <= 5 humans), register-resident ORCA solver.
+// step_flat.cuh -- CrowdSim step for small crowds (N <= 5 humans), register-resident ORCA solver, 1 .. n steps per launch.
 //
 // Same contract as step_kernel (crowd_sim/envs/crowd_sim.py:317-420 + orca.py:82-132 + explorer.py:41-72).
 // Mapping: one thread per (env, agent) solve, L = N + 1 lanes per env, floor(32 / L) whole envs per warp so an env
@@ -7,20 +7,30 @@
 // done with warp shuffles -- no shared-memory staging, no block barrier on the common path.
 // The <= N ORCA lines of a solve live in REGISTERS: every loop over lines is fully unrolled (template on N), so
 // the LP code has static register indexing, no local/shared memory traffic and instruction-level parallelism
-// across the independent (i, j) line pairs.
+// across the independent (i, j) line pairs (speculative lp1 candidates + lp2 as a scan, orca_spec.cuh).
+//
 // linearProgram3 (needed by ~4.6 % of the solves, i.e. by some lane of ~3 of 4 warps) is NOT run in place: the
 // solves that need it are compacted into a shared-memory queue. Inside linearProgram3 the sub-problem of each line i
 // (linearProgram2 over the lines projected onto i, started from optVelocity * radius) depends only on the lines, not
 // on the running result, so the <= N-1 sub-problems of a queued solve run on N-1 LANES IN PARALLEL (the sequential
-// shared-memory LP code of orca_device.cuh), followed by a 4-step scan. Before this, the pass was a ~1500-instruction
-// serial chain on a handful of lanes with the whole block waiting: ~4.5 of 14 us per launch.
+// shared-memory LP code of orca_device.cuh), followed by a 4-step scan.
 // The queue is per BLOCK (WARPQ = false: one warp runs the pass for the whole block, the others wait at a barrier;
 // fewest instructions, best when the launch fills the chip) or per WARP (WARPQ = true: no block barrier, every warp runs
 // the pass for its own 1-2 solves; best for launches that leave the SMs mostly empty). cs::launch() picks by grid size.
+// Round 2 measured two finer splits of the pass, both bit-identical, both SLOWER, neither kept (profiles/r02_lp3_lanes.txt):
+// (a) projections on (i, j) lanes + register-resident speculative sub-problems (orca_spec.cuh: lp3_project_pair /
+// lp3_sub_spec, host-fuzzed): pass 4.4 vs 3.1 us at 4096 envs, 400 vs 162 us at 1 Mi envs; (b) four lane levels with
+// early-exit code (projections, lp1 candidates, lp2 scans, outer scan; 10 lanes per item): 4.2 us / 195 us. More lanes
+// per item means more warps with active lanes = more warp-instructions for the same work, and the all-pairs speculative
+// form executes more instructions than early-exit code; at 1-2 warps per scheduler a warp's time is its instruction count.
 //
-// Evidence that motivated this design (profiles/r01_*): one-thread-per-agent with shared-memory lines ran at 13.6/32
-// active lanes and 3480 instructions per warp; the warp-per-env cooperative variant needed 1750 warp instructions
-// per env. This kernel needs 483 per env (2.4 k per warp of 5 envs) at 23/32 active lanes.
+// MULTI = true: crowdsim_step_n. With an ORCA robot nothing leaves the device between steps (explorer.py:41-43 is a pure
+// loop), so a launch advances its envs n steps with the state in REGISTERS: one load of the state, n x (solve, collision,
+// ladder, bookkeeping, install of the prefetched next scene when an episode ends), one store. That removes the launch gap
+// and the load/store stage from every step but the first. Results are bit-identical to n x crowdsim_step.
+//
+// Memory effects are written once at the end of the launch from the registers (both modes); rare events (an episode's
+// result row, parking, slot hand-over) are written when they happen.
 #pragma once
 #include "crowdsim_common.cuh"
 #include "orca_spec.cuh"
@@ -32,33 +42,32 @@ namespace cs {
 // EPW = 32 / (N + 1) whole envs per warp (dense packing; sparser packings were measured and are never faster,
 // profiles/r01_tune_epw_n5.txt). STAGE is a profiling aid (scripts/latency_probe.cu instantiates cut-down variants to
 // attribute latency); the library only instantiates the full kernel (STAGE = 99).
-// Register budget: asking for 6 resident blocks per SM (<= 80 registers, a few bytes of spill) is neutral at 4096 envs and
-// 9 % faster at 65 k .. 1 M envs than the unconstrained 90-register build (scripts/latency_probe.cu, -DCS_FLAT_MINBLOCKS=1/6/8).
-// CS_FLAT_WPB = warps per block, CS_FLAT_MINBLOCKS = resident-blocks hint (per 128 threads), CS_FLAT_WARP_LP3 = default of the
-// WARPQ template parameter: build-time knobs for A/B runs (scripts/gpu_variants.sh); 4 / 6 / size-dependent were kept.
-// EXPERIMENT: -DCS_FLAT_NO_ROT compiles the unicycle-robot trigonometry out of the small-crowd kernel
-// (~12 % of its SASS, never executed by holonomic robots) to measure what the instruction-fetch stalls cost; such a build
-// only serves holonomic / ORCA robots. Default: runtime test, as the reference's agent.py:115-135.
-#ifdef CS_FLAT_NO_ROT
-#define CS_FLAT_IS_ROT(k) false
-#else
-#define CS_FLAT_IS_ROT(k) ((k).robot_policy == CROWDSIM_ROBOT_EXTERNAL_ROT)
-#endif
+// Register budget of the single-step kernel: 6 resident blocks per SM (<= 80 registers) is neutral at 4096 envs and 9 %
+// faster at 65 k .. 1 M envs than the unconstrained build (round 1); the multi-step kernel serves launches that leave
+// the chip mostly empty and carries ~35 registers of state across steps: 3 blocks per SM (<= 168 registers).
+// ROT: the robot is a unicycle (CROWDSIM_ROBOT_EXTERNAL_ROT, agent.py:115-135). A template parameter so that the double
+// precision cos / sin / fmod code (12 % of the round-1 kernel's SASS) is only present in the kernels that execute it.
 #ifndef CS_FLAT_WPB
 #define CS_FLAT_WPB 4
-#endif
-#ifndef CS_FLAT_WARP_LP3
-#define CS_FLAT_WARP_LP3 0
 #endif
 #ifndef CS_FLAT_MINBLOCKS
 #define CS_FLAT_MINBLOCKS 6
 #endif
-template <int N, int STAGE = 99, bool WARPQ = (CS_FLAT_WARP_LP3 != 0)>
-__global__ void __launch_bounds__(32 * CS_FLAT_WPB, CS_FLAT_MINBLOCKS * 4 / CS_FLAT_WPB) step_flat_kernel(const __grid_constant__ StepArgs A)
+#ifndef CS_FLAT_MINBLOCKS_MULTI
+#define CS_FLAT_MINBLOCKS_MULTI 3
+#endif
+
+template <int N, int STAGE = 99, bool ROT = false, bool MULTI = false, bool WARPQ = MULTI>
+__global__ void __launch_bounds__(32 * CS_FLAT_WPB, (MULTI ? CS_FLAT_MINBLOCKS_MULTI : CS_FLAT_MINBLOCKS) * 4 / CS_FLAT_WPB)
+step_flat_kernel(const __grid_constant__ StepArgs A)
 {
+    static_assert(STAGE == 99 || !MULTI, "stage cut-offs exist for the single-step kernel only");
+    static_assert(!(ROT && MULTI), "a unicycle robot needs an external action every step");
+    static_assert(WARPQ || !MULTI, "the multi-step kernel has no block barrier: warps run ahead of each other");
     if constexpr (STAGE == 0) return;
     using namespace orca;
-    constexpr int L = N + 1, M = N, EPW = 32 / L, WPB = CS_FLAT_WPB, T = 32 * WPB;
+    constexpr int L = N + 1, M = N, EPW = 32 / L, WPB = CS_FLAT_WPB;
+    constexpr int T = 32 * WPB;
     constexpr int SUB = (M > 1) ? M - 1 : 1;                // lanes per queued lp3 item (sub-problems i = 1 .. M-1)
     constexpr int QF = 4 * M + 5;                           // floats per queued lp3 work item
     __shared__ float s_q[QF][T];                            // [field][slot]: lines of an item = orca::Lines(base = &s_q[0][slot], stride = T)
@@ -71,13 +80,15 @@ __global__ void __launch_bounds__(32 * CS_FLAT_WPB, CS_FLAT_MINBLOCKS * 4 / CS_F
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     const int le = lane / L, a = lane - le * L;             // env within the warp, agent within the env
     const int ebase = le * L;                               // first lane of my env
+    const int rl = ebase + N;                               // my env's robot lane
     const int e = (blockIdx.x * WPB + wib) * EPW + le;
     const bool is_robot = (a == N);
     const bool env_ok = (le < EPW) && (e < A.B);
-    if (tid == 0) s_qcount = 0;
+    const size_t hi = (size_t)e * N + a;                    // my element of the [B][N][2] arrays (human lanes)
+    if (!WARPQ && tid == 0) s_qcount = 0;
 
-    // ---- all global loads of the step are issued up front, unconditionally for valid envs, so that they overlap into ONE
-    // DRAM round trip (active flag -> state -> episode accumulators / slot state used to be dependent ones) ----
+    // ---- all global loads of the launch are issued up front, unconditionally for valid envs, so that they overlap into ONE
+    // DRAM round trip ----
     // (idle lanes get a goal 5 m away: a zero goal vector would drag the warp through the f64 sqrt / division slow paths)
     double2 pos = make_double2(0, 0), vel = pos, goal = make_double2(3, 4), attr = make_double2(0.3, 1.0);
     double theta = 0, gtime = 0; double2 ext = make_double2(0, 0);
@@ -86,22 +97,35 @@ __global__ void __launch_bounds__(32 * CS_FLAT_WPB, CS_FLAT_MINBLOCKS * 4 / CS_F
     if (env_ok) {
         if (A.st.active) act_flag = A.st.active[e];
         if (!is_robot) {
-            const size_t i = (size_t)e * N + a;
-            pos = ld2(A.st.h_pos, i); vel = ld2(A.st.h_vel, i); goal = ld2(A.st.h_goal, i); attr = ld2(A.st.h_attr, i);
+            pos = ld2(A.st.h_pos, hi); vel = ld2(A.st.h_vel, hi); goal = ld2(A.st.h_goal, hi); attr = ld2(A.st.h_attr, hi);
         } else {
             pos = ld2(A.st.r_pos, e); vel = ld2(A.st.r_vel, e); goal = ld2(A.st.r_goal, e); attr = ld2(A.st.r_attr, e);
             gtime = A.st.g_time[e];
-            if (CS_FLAT_IS_ROT(k)) theta = A.st.r_theta[e];
+            if (ROT) theta = A.st.r_theta[e];
             if (k.robot_policy != CROWDSIM_ROBOT_ORCA) ext = ld2(A.io.action, e);
             if (A.has_ep) { ep_t = A.ep.ep_steps[e]; ep_ret = A.ep.ep_return[e]; ep_tc = A.ep.ep_too_close[e]; ep_mds = A.ep.ep_min_dist_sum[e]; ep_c = A.ep.ep_case[e]; }
-            if (A.has_ar) { slot_state = *reinterpret_cast<volatile uint8_t *>(A.ar.n_state + e); want_flag = A.ar.want[e]; }
+            if (A.has_ar) { if (!MULTI) slot_state = ld_relaxed_u8(A.ar.n_state + e); want_flag = A.ar.want[e]; }
         }
     }
-    const bool live = env_ok && (act_flag != 0);
     if constexpr (STAGE == 1) {            // loads + stores only
-        if (live && !is_robot) { const size_t i = (size_t)e * N + a; st2(A.st.h_pos, i, pos); st2(A.st.h_vel, i, make_double2(vel.x + goal.x * 0, vel.y + attr.x * 0)); }
-        if (live && is_robot) { st2(A.st.r_pos, e, pos); A.st.g_time[e] = gtime + ext.x * 0 + theta * 0; }
+        const bool live1 = env_ok && (act_flag != 0);
+        if (live1 && !is_robot) { st2(A.st.h_pos, hi, pos); st2(A.st.h_vel, hi, make_double2(vel.x + goal.x * 0, vel.y + attr.x * 0)); }
+        if (live1 && is_robot) { st2(A.st.r_pos, e, pos); A.st.g_time[e] = gtime + ext.x * 0 + theta * 0; }
         return;
+    }
+
+    // what this launch changed (decides the stores at the end)
+    bool dirty_kin = false, dirty_scene = false, dirty_ep = false, any_live = false, new_case = false;
+    double o_reward = 0, o_dmin = 0; double2 o_act = make_double2(0, 0); int o_done = 0, o_info = 0;
+    const double dt = k.time_step;
+
+    const int n_steps = MULTI ? A.n_steps : 1;
+    #pragma unroll 1
+    for (int s = 0; s < n_steps; ++s) {
+    const bool live = env_ok && (act_flag != 0);
+    if constexpr (MULTI) {
+        // nothing left to do for this warp: every env is frozen and none is waiting for a scene
+        if (__ballot_sync(CS_FULL, live || (is_robot && env_ok && want_flag != 0 && A.has_ar)) == 0u) break;
     }
     // float32 view of myself for the other lanes of my env (rvo2 boundary casts, orca.py:100-110)
     const float fpx = (float)pos.x, fpy = (float)pos.y, fvx = (float)vel.x, fvy = (float)vel.y;
@@ -132,8 +156,8 @@ __global__ void __launch_bounds__(32 * CS_FLAT_WPB, CS_FLAT_MINBLOCKS * 4 / CS_F
     }
     // rank of each candidate = position RVO2's insertion sort (strict <, ties in scan order) would give it: for cc < c,
     // cc precedes c iff dsq[cc] <= dsq[c] -- one comparison per unordered pair. The agent index of the kk-th nearest is
-    // then read from a packed word (3 bits per position, N <= 5) instead of an M x M select cascade; together 7 % fewer
-    // instructions per warp than the 2 M^2 compare-and-select form (ncu source view, step_flat.cuh:130/134 before).
+    // then read from a packed word (3 bits per position, N <= 5) instead of an M x M select cascade (orca_spec.cuh:
+    // neighbour_order is the host-checked copy of these statements).
     int rank[M];
     #pragma unroll
     for (int c = 0; c < M; ++c) rank[c] = 0;
@@ -141,9 +165,9 @@ __global__ void __launch_bounds__(32 * CS_FLAT_WPB, CS_FLAT_MINBLOCKS * 4 / CS_F
     for (int c = 1; c < M; ++c) {
         #pragma unroll
         for (int cc = 0; cc < c; ++cc) {
-            const bool le = dsq[cc] <= dsq[c];
-            rank[c] += (inr[cc] && le) ? 1 : 0;
-            rank[cc] += (inr[c] && !le) ? 1 : 0;
+            const bool le_ = dsq[cc] <= dsq[c];
+            rank[c] += (inr[cc] && le_) ? 1 : 0;
+            rank[cc] += (inr[c] && !le_) ? 1 : 0;
         }
     }
     int nl = 0; unsigned packed = 0u;
@@ -166,24 +190,27 @@ __global__ void __launch_bounds__(32 * CS_FLAT_WPB, CS_FLAT_MINBLOCKS * 4 / CS_F
         R.p[kk] = mk(0.f, 0.f); R.d[kk] = mk(0.f, 0.f);
         if (valid[kk]) make_line_sel(p, v, r, mk(qx, qy), mk(wx, wy), is_robot ? rr : rh, k.inv_time_horizon, k.inv_time_step, R.p[kk], R.d[kk]);
     }
-
-    // ---- linear programs: lp2 in place, lp3 deferred to the block-compacted pass ----
     if constexpr (STAGE == 2) {            // + preferred velocity, neighbour scan, ORCA lines
         float acc = pref.x + pref.y;
         #pragma unroll
         for (int kk = 0; kk < M; ++kk) acc += R.p[kk].x + R.p[kk].y + R.d[kk].x + R.d[kk].y;
-        if (live && !is_robot) { const size_t i = (size_t)e * N + a; st2(A.st.h_vel, i, make_double2(vel.x, vel.y + (double)acc * 0)); }
+        if (live && !is_robot) st2(A.st.h_vel, hi, make_double2(vel.x, vel.y + (double)acc * 0));
         return;
     }
-    // speculative lp1 candidates for every line (orca_spec.cuh), then linearProgram2 as a scan
+
+    // ---- linear programs: speculative lp1 candidates for every line (orca_spec.cuh), then linearProgram2 as a scan ----
     V2 cand[M]; bool feas[M];
     lp1_all<M, M>(R, valid, max_speed, pref, false, cand, feas);
     V2 nv = mk(0.f, 0.f);
     const int fail = lp2_scan<M, M>(R, valid, nl, cand, feas, lp2_init(pref, max_speed), nv);
     if constexpr (STAGE == 3) {            // + lp1 candidates and the lp2 scan
-        if (live && !is_robot) { const size_t i = (size_t)e * N + a; st2(A.st.h_vel, i, make_double2(vel.x + (double)nv.x * 0, vel.y + (double)(nv.y + fail) * 0)); }
+        if (live && !is_robot) st2(A.st.h_vel, hi, make_double2(vel.x + (double)nv.x * 0, vel.y + (double)(nv.y + fail) * 0));
         return;
     }
+
+    // ---- linearProgram3: the solves that need it are compacted into a shared-memory queue; the sub-problems of an item
+    // run on SUB lanes in parallel (sequential shared-memory LP code of orca_device.cuh), one lane finishes with
+    // linearProgram3's outer scan ----
     const bool need3 = solves && fail < nl;
     if constexpr (WARPQ) {
         // warp-level queue: no block barrier; every warp runs the sub-problems of its own solves
@@ -223,15 +250,16 @@ __global__ void __launch_bounds__(32 * CS_FLAT_WPB, CS_FLAT_MINBLOCKS * 4 / CS_F
                     const float qr = s_q[4 * M + 2][item];
                     V2 res = mk(s_q[4 * M + 3][item], s_q[4 * M + 4][item]);
                     lp3_outer_scan(Lq, qn, qf, qr, res, [&](int ii, V2 &r2) {
-                        const int src = tid + (ii - 1);
-                        r2 = mk(s_r2[0][src], s_r2[1][src]);
-                        return s_r2[2][src] != 0.0f;
+                        const int src_ = tid + (ii - 1);
+                        r2 = mk(s_r2[0][src_], s_r2[1][src_]);
+                        return s_r2[2][src_] != 0.0f;
                     });
                     s_res[0][item] = res.x; s_res[1][item] = res.y;
                 }
                 __syncwarp();
             }
             if (need3) nv = mk(s_res[0][slot], s_res[1][slot]);
+            __syncwarp();                                        // the queue is reused by the next step (MULTI)
         }
     } else {
         __syncthreads();                                         // s_qcount = 0 visible
@@ -257,8 +285,8 @@ __global__ void __launch_bounds__(32 * CS_FLAT_WPB, CS_FLAT_MINBLOCKS * 4 / CS_F
                     const int qn = __float_as_int(s_q[4 * M + 0][item]);
                     bool ok = false; V2 r2 = mk(0.f, 0.f);
                     if (M > 1 && i < qn) {
-                        // sequential shared-memory LP code (early exits): measured faster here than a register-resident
-                        // speculative version of the sub-problem (LP3 stage 3.5 vs 4.5 us at 4096 envs)
+                        // sequential shared-memory LP code with early exits: measured faster here than every finer or
+                        // speculative split tried (header; profiles/r02_lp3_lanes.txt)
                         const Lines Pq = { &s_p[0][tid], T };
                         ok = lp3_subproblem(Lq, i, s_q[4 * M + 2][item], Pq, r2);
                     }
@@ -271,9 +299,9 @@ __global__ void __launch_bounds__(32 * CS_FLAT_WPB, CS_FLAT_MINBLOCKS * 4 / CS_F
                     const float qr = s_q[4 * M + 2][item];
                     V2 res = mk(s_q[4 * M + 3][item], s_q[4 * M + 4][item]);
                     lp3_outer_scan(Lq, qn, qf, qr, res, [&](int ii, V2 &r2) {
-                        const int src = tid + (ii - 1);               // lane of sub-problem ii of this item
-                        r2 = mk(s_r2[0][src], s_r2[1][src]);
-                        return s_r2[2][src] != 0.0f;
+                        const int src_ = tid + (ii - 1);              // lane of sub-problem ii of this item
+                        r2 = mk(s_r2[0][src_], s_r2[1][src_]);
+                        return s_r2[2][src_] != 0.0f;
                     });
                     s_res[0][item] = res.x; s_res[1][item] = res.y;
                 }
@@ -283,32 +311,32 @@ __global__ void __launch_bounds__(32 * CS_FLAT_WPB, CS_FLAT_MINBLOCKS * 4 / CS_F
         }
     }
 
-    if (A.act_only) {                      // crowdsim_orca_act: the robot's ORCA decision only, nothing is mutated
-        if (live && is_robot) st2(A.io.action_out, e, make_double2((double)nv.x, (double)nv.y));
-        return;
+    if constexpr (!MULTI) {
+        if (A.act_only) {                  // crowdsim_orca_act: the robot's ORCA decision only, nothing is mutated
+            if (live && is_robot) st2(A.io.action_out, e, make_double2((double)nv.x, (double)nv.y));
+            return;
+        }
     }
     if constexpr (STAGE == 4) {            // + lp3
-        if (live && !is_robot) { const size_t i = (size_t)e * N + a; st2(A.st.h_vel, i, make_double2(vel.x + (double)nv.x * 0, vel.y + (double)nv.y * 0)); }
+        if (live && !is_robot) st2(A.st.h_vel, hi, make_double2(vel.x + (double)nv.x * 0, vel.y + (double)nv.y * 0));
         return;
     }
     // ---- robot velocity of this step, broadcast inside the env ----
     double ax = 0, ay = 0, rvx = 0, rvy = 0;
     if (is_robot) {
         if (k.robot_policy == CROWDSIM_ROBOT_ORCA) { ax = (double)nv.x; ay = (double)nv.y; rvx = ax; rvy = ay; }
-        else if (CS_FLAT_IS_ROT(k)) { ax = ext.x; ay = ext.y; rvx = ax * cos(ay + theta); rvy = ax * sin(ay + theta); }
+        else if (ROT) { ax = ext.x; ay = ext.y; rvx = ax * cos(ay + theta); rvy = ax * sin(ay + theta); }      // crowd_sim.py:340-341
         else { ax = ext.x; ay = ext.y; rvx = ax; rvy = ay; }
     }
-    const int rl = ebase + N;                                // my env's robot lane
     const double Rvx = __shfl_sync(CS_FULL, rvx, rl), Rvy = __shfl_sync(CS_FULL, rvy, rl);
     const double Rpx = __shfl_sync(CS_FULL, pos.x, rl), Rpy = __shfl_sync(CS_FULL, pos.y, rl);
     const double Rrad = __shfl_sync(CS_FULL, attr.x, rl);
 
-    // ---- human lanes: swept-segment clearance (crowd_sim.py:333-345) + Euler step (agent.py:122-135) ----
-    const double dt = k.time_step;
+    // ---- human lanes: swept-segment clearance (crowd_sim.py:333-345) ----
     double closest = 0.0;
     if (live && !is_robot) {
         const double px = pos.x - Rpx, py = pos.y - Rpy;
-        const double vx = vel.x - Rvx, vy = vel.y - Rvy;
+        const double vx = vel.x - Rvx, vy = vel.y - Rvy;    // the human's CURRENT velocity attribute (previous action)
         const double ex = px + vx * dt, ey = py + vy * dt;
         closest = point_to_segment_dist0(px, py, ex, ey) - attr.x - Rrad;
     }
@@ -320,13 +348,14 @@ __global__ void __launch_bounds__(32 * CS_FLAT_WPB, CS_FLAT_MINBLOCKS * 4 / CS_F
         if (!collision) { if (ci < 0) collision = true; else if (ci < dmin) dmin = ci; }
     }
 
-    // ---- robot lane: ladder, update, bookkeeping; decides about auto-reset ----
+    // ---- robot lane: ladder (crowd_sim.py:365-389), update (agent.py:110-135), bookkeeping (explorer.py:41-72);
+    // decides about auto-reset ----
     int install = 0;
     if (is_robot && env_ok) {
         bool done = false;
         if (live) {
             double npx, npy, nvx, nvy;
-            if (!CS_FLAT_IS_ROT(k)) { npx = pos.x + ax * dt; npy = pos.y + ay * dt; nvx = ax; nvy = ay; }
+            if (!ROT) { npx = pos.x + ax * dt; npy = pos.y + ay * dt; nvx = ax; nvy = ay; }
             else { const double th = theta + ay; npx = pos.x + cos(th) * ax * dt; npy = pos.y + sin(th) * ax * dt; nvx = nvy = 0; }
             const bool reaching_goal = norm2(npx - goal.x, npy - goal.y) < attr.x;
             double reward; int info;
@@ -335,49 +364,97 @@ __global__ void __launch_bounds__(32 * CS_FLAT_WPB, CS_FLAT_MINBLOCKS * 4 / CS_F
             else if (reaching_goal) { reward = k.success_reward; done = true; info = CROWDSIM_INFO_REACHGOAL; }
             else if (dmin < k.discomfort_dist) { reward = (dmin - k.discomfort_dist) * k.discomfort_penalty_factor * dt; done = false; info = CROWDSIM_INFO_DANGER; }
             else { reward = 0; done = false; info = CROWDSIM_INFO_NOTHING; }
-            if (CS_FLAT_IS_ROT(k)) {
+            if (ROT) {                                                                   // agent.py:133-135
                 double nth = fmod(theta + ay, 2 * CS_PI); if (nth < 0) nth += 2 * CS_PI;
-                A.st.r_theta[e] = nth; nvx = ax * cos(nth); nvy = ax * sin(nth);
+                theta = nth; nvx = ax * cos(nth); nvy = ax * sin(nth);
             }
-            st2(A.st.r_pos, e, make_double2(npx, npy));
-            st2(A.st.r_vel, e, make_double2(nvx, nvy));
-            const double ntime = gtime + dt;
-            A.st.g_time[e] = ntime;
-            if (A.io.action_out) st2(A.io.action_out, e, make_double2(nvx, nvy));
-            A.io.reward[e] = reward; A.io.dmin[e] = dmin; A.io.done[e] = done ? 1 : 0; A.io.info[e] = (uint8_t)info;
+            pos = make_double2(npx, npy); vel = make_double2(nvx, nvy);
+            gtime = gtime + dt;
+            if constexpr (MULTI) { o_act = vel; o_reward = reward; o_dmin = dmin; o_done = done ? 1 : 0; o_info = info; any_live = true; }
+            else {                                           // single step: nothing to carry, the outputs leave at once
+                if (A.io.action_out) st2(A.io.action_out, e, vel);
+                A.io.reward[e] = reward; A.io.dmin[e] = dmin; A.io.done[e] = done ? 1 : 0; A.io.info[e] = (uint8_t)info;
+            }
+            dirty_kin = true;
             if (A.has_ep) {
                 const crowdsim_episodes &ep = A.ep;
-                const int t = ep_t;
-                const double disc = (t < ep.discount_len) ? ep.discount[t] : 0.0;
-                const double ret = ep_ret + disc * reward;
-                int tc = ep_tc; double mds = ep_mds;
-                if (info == CROWDSIM_INFO_DANGER) { tc += 1; mds += dmin; ep.ep_too_close[e] = tc; ep.ep_min_dist_sum[e] = mds; }
-                ep.ep_return[e] = ret; ep.ep_steps[e] = t + 1;
+                const double disc = (ep_t < ep.discount_len) ? ep.discount[ep_t] : 0.0;
+                ep_ret = ep_ret + disc * reward; ep_t += 1;
+                if (info == CROWDSIM_INFO_DANGER) { ep_tc += 1; ep_mds += dmin; }
+                dirty_ep = true;
                 if (done) {
-                    const int cs_ = ep_c;
-                    if (cs_ >= 0) {
-                        ep.res_info[cs_] = (uint8_t)info; ep.res_steps[cs_] = t + 1;
-                        ep.res_time[cs_] = (info == CROWDSIM_INFO_TIMEOUT) ? k.time_limit : ntime;
-                        ep.res_return[cs_] = ret; ep.res_too_close[cs_] = tc; ep.res_min_dist_sum[cs_] = mds;
-                        if (ep.res_final_rpos) st2(ep.res_final_rpos, cs_, make_double2(npx, npy));
+                    if (ep_c >= 0) {
+                        ep.res_info[ep_c] = (uint8_t)info; ep.res_steps[ep_c] = ep_t;
+                        ep.res_time[ep_c] = (info == CROWDSIM_INFO_TIMEOUT) ? k.time_limit : gtime;
+                        ep.res_return[ep_c] = ep_ret; ep.res_too_close[ep_c] = ep_tc; ep.res_min_dist_sum[ep_c] = ep_mds;
+                        if (ep.res_final_rpos) st2(ep.res_final_rpos, ep_c, pos);
                     }
-                    if (A.st.active && !A.has_ar) A.st.active[e] = 0;
+                    if (A.st.active && !A.has_ar) { A.st.active[e] = 0; act_flag = 0; }
                 }
             }
         }
-        if (A.has_ar) install = ar_decide(A, e, slot_state, live && done, !live && want_flag != 0);
+        if (A.has_ar) {
+            // consumer side of the auto-reset protocol (include/crowdsim_b200.h): an env that just finished, or is parked
+            // waiting, looks at its next-scene slot; a slot the generator publishes later is picked up by a later step
+            const bool finished = live && done, parked = !live && want_flag != 0;
+            if (finished || parked) {
+                const uint8_t sst = MULTI ? ld_relaxed_u8(A.ar.n_state + e) : slot_state;
+                if (sst == CROWDSIM_SLOT_READY) install = 1;
+                else {
+                    act_flag = 0; A.st.active[e] = 0;                             // park: nothing to install (yet)
+                    want_flag = (sst == CROWDSIM_SLOT_EXHAUSTED) ? 0 : 1; A.ar.want[e] = want_flag;
+                }
+            }
+        }
     }
     if (A.has_ar) {                                          // warp-uniform
         install = __shfl_sync(CS_FULL, install, rl) && env_ok;
-        if (install) { if (is_robot) ar_install_robot(A, e); else ar_install_human(A, e, N, a); }
+        if (install) {
+            // acquire on the slot flag (every lane that reads slot data), then the scene (agent.py:47-58 set(px,py,gx,gy,0,0,..))
+            (void)ld_acquire_u8(A.ar.n_state + e);
+            if (!is_robot) {
+                pos = ld2_cg(A.ar.n_h_pos, hi); vel = make_double2(0, 0); goal = ld2_cg(A.ar.n_h_goal, hi); attr = ld2_cg(A.ar.n_h_attr, hi);
+            } else {                                         // crowd_sim.py:262,274 + fresh episode accumulators
+                pos = make_double2(0.0, -A.ar.circle_radius); goal = make_double2(0.0, A.ar.circle_radius);
+                vel = make_double2(0, 0); attr = make_double2(A.ar.robot_radius, A.ar.robot_v_pref);
+                theta = CS_PI / 2; gtime = 0.0;
+                if (!ROT && A.st.r_theta) A.st.r_theta[e] = CS_PI / 2;
+                if (A.has_ep) { ep_t = 0; ep_ret = 0.0; ep_tc = 0; ep_mds = 0.0; ep_c = __ldcg(A.ar.n_case + e); dirty_ep = true; new_case = true; }
+                act_flag = 1; A.st.active[e] = 1; want_flag = 0; A.ar.want[e] = 0;
+            }
+            dirty_kin = true; dirty_scene = true;
+        }
         __syncwarp();
-        if (install && is_robot) *reinterpret_cast<volatile uint8_t *>(A.ar.n_state + e) = CROWDSIM_SLOT_EMPTY;
+        if (install && is_robot) st_release_u8(A.ar.n_state + e, CROWDSIM_SLOT_EMPTY);     // slot data consumed by all lanes of the env
+        if (MULTI) act_flag = (uint8_t)__shfl_sync(CS_FULL, (int)act_flag, rl);           // human lanes follow their robot lane's flag
+    } else if (MULTI) {
+        act_flag = (uint8_t)__shfl_sync(CS_FULL, (int)act_flag, rl);
     }
     if (live && !is_robot && !install) {
+        // agent.py:122-135 holonomic step with the ORCA action (float32 values widened)
         const double hx = (double)nv.x, hy = (double)nv.y;
-        const size_t i = (size_t)e * N + a;
-        st2(A.st.h_pos, i, make_double2(pos.x + hx * dt, pos.y + hy * dt));
-        st2(A.st.h_vel, i, make_double2(hx, hy));
+        pos = make_double2(pos.x + hx * dt, pos.y + hy * dt); vel = make_double2(hx, hy);
+        dirty_kin = true;
+    }
+    }   // step loop
+
+    // ---- one store of everything this launch changed ----
+    if (env_ok) {
+        if (!is_robot) {
+            if (dirty_kin) { st2(A.st.h_pos, hi, pos); st2(A.st.h_vel, hi, vel); }
+            if (dirty_scene) { st2(A.st.h_goal, hi, goal); st2(A.st.h_attr, hi, attr); }
+        } else {
+            if (dirty_kin) { st2(A.st.r_pos, e, pos); st2(A.st.r_vel, e, vel); A.st.g_time[e] = gtime; if (ROT) A.st.r_theta[e] = theta; }
+            if (dirty_scene) { st2(A.st.r_goal, e, goal); st2(A.st.r_attr, e, attr); }
+            if (MULTI && any_live) {                         // outputs of the env's last live step
+                if (A.io.action_out) st2(A.io.action_out, e, o_act);
+                A.io.reward[e] = o_reward; A.io.dmin[e] = o_dmin; A.io.done[e] = (uint8_t)o_done; A.io.info[e] = (uint8_t)o_info;
+            }
+            if (A.has_ep && dirty_ep) {
+                A.ep.ep_steps[e] = ep_t; A.ep.ep_return[e] = ep_ret; A.ep.ep_too_close[e] = ep_tc; A.ep.ep_min_dist_sum[e] = ep_mds;
+                if (new_case) A.ep.ep_case[e] = ep_c;
+            }
+        }
     }
 }
 

@@ -18,7 +18,6 @@ namespace cs {
 
 unsigned long long g_launches = 0;
 int g_force_generic = 0;   // test hook: route every N through the generic one-thread-per-agent kernel
-int g_lp3_queue = -1;      // test / tuning hook: -1 = pick the small-crowd kernel's lp3 queue by grid size, 0 = per block, 1 = per warp
 
 struct StepArgs {
     KParams k;
@@ -29,6 +28,7 @@ struct StepArgs {
     crowdsim_autoreset ar;
     int has_ep, has_ar;
     int act_only;      // crowdsim_orca_act: robot lanes solve and write action_out, nothing is mutated
+    int n_steps;       // crowdsim_step_n: env-steps per launch (small-crowd kernel, ORCA robot)
 };
 
 // ---- auto-reset protocol, consumer side (include/crowdsim_b200.h: crowdsim_autoreset) ----
@@ -44,18 +44,19 @@ __device__ __forceinline__ int ar_decide(const StepArgs &A, int e, uint8_t s, bo
     return 0;
 }
 // Human lane a of env e: copy the prefetched scene into the live state (agent.py:47-58 set(px,py,gx,gy,0,0,...)).
-// The generator published the slot with (data, __threadfence, flag); the flag was read volatile at kernel start, the data
-// is read here with ld.global.cg (L2 = coherence point, no stale L1 line possible), so no reader-side fence is needed.
-__device__ __forceinline__ double2 ld2_cg(const double *p, size_t i) { return __ldcg(reinterpret_cast<const double2 *>(p) + i); }
+// The generator published the slot with st.release; every lane that reads slot data acquires the flag first (and reads
+// with ld.global.cg: L2 is the coherence point).
 __device__ __forceinline__ void ar_install_human(const StepArgs &A, int e, int N, int a)
 {
     const size_t i = (size_t)e * N + a;
+    (void)ld_acquire_u8(A.ar.n_state + e);
     st2(A.st.h_pos, i, ld2_cg(A.ar.n_h_pos, i)); st2(A.st.h_vel, i, make_double2(0, 0));
     st2(A.st.h_goal, i, ld2_cg(A.ar.n_h_goal, i)); st2(A.st.h_attr, i, ld2_cg(A.ar.n_h_attr, i));
 }
 // Robot lane of env e: crowd_sim.py:262,274 (global_time = 0, robot.set(0,-R,0,R,0,0,pi/2)) + fresh episode accumulators.
 __device__ __forceinline__ void ar_install_robot(const StepArgs &A, int e)
 {
+    (void)ld_acquire_u8(A.ar.n_state + e);
     st2(A.st.r_pos, e, make_double2(0.0, -A.ar.circle_radius)); st2(A.st.r_goal, e, make_double2(0.0, A.ar.circle_radius));
     st2(A.st.r_vel, e, make_double2(0, 0)); st2(A.st.r_attr, e, make_double2(A.ar.robot_radius, A.ar.robot_v_pref));
     if (A.st.r_theta) A.st.r_theta[e] = CS_PI / 2;
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepA
                 }
             }
         }
-        if (A.has_ar) install = ar_decide(A, e, *reinterpret_cast<volatile uint8_t *>(A.ar.n_state + e), live && done, !live && A.ar.want[e] != 0);
+        if (A.has_ar) install = ar_decide(A, e, ld_relaxed_u8(A.ar.n_state + e), live && done, !live && A.ar.want[e] != 0);
     }
     if (A.has_ar) {
         if (is_robot) s.closest[le * L + N] = (double)install;     // the robot's own clearance slot is unused: env-wide flag
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepA
         install = (s.closest[le * L + N] != 0.0) && env_ok;
         if (install) { if (is_robot) ar_install_robot(A, e); else ar_install_human(A, e, N, a); }
         __syncthreads();
-        if (install && is_robot) *reinterpret_cast<volatile uint8_t *>(A.ar.n_state + e) = CROWDSIM_SLOT_EMPTY;
+        if (install && is_robot) st_release_u8(A.ar.n_state + e, CROWDSIM_SLOT_EMPTY);
     }
     if (live && !is_robot && !install) {
         // agent.py:122-135 holonomic step with the ORCA action (float32 values widened)
@@ -214,10 +215,20 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepA
 // more, less divergent warps, but were measured on B200 at 1 k .. 1 M envs and are never faster: the kernel's instruction
 // stream is almost data-independent, so sparse warps only multiply the instruction count (profiles/r01_tune_epw_n5.txt).
 
-static int launch(const crowdsim_params *prm, int B, int N, const crowdsim_state *st, const crowdsim_step_io *io,
-                  const crowdsim_episodes *ep, const crowdsim_autoreset *ar, int act_only, cudaStream_t stream)
+// SM count of the CURRENT device (cached per device: a process may drive several GPUs).
+static int sm_count()
 {
-    if (!prm || !st || !io || B < 0 || N < 0) return CROWDSIM_EINVAL;
+    static int cache[64];
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 148;
+    if (cache[dev] == 0) { int n = 0; cache[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148; }
+    return cache[dev];
+}
+
+static int launch(const crowdsim_params *prm, int B, int N, const crowdsim_state *st, const crowdsim_step_io *io,
+                  const crowdsim_episodes *ep, const crowdsim_autoreset *ar, int act_only, int n_steps, cudaStream_t stream)
+{
+    if (!prm || !st || !io || B < 0 || N < 0 || n_steps < 1) return CROWDSIM_EINVAL;
     if (N > CROWDSIM_MAX_HUMANS || prm->max_neighbors > CROWDSIM_MAX_NEIGHBORS) return CROWDSIM_EUNSUPPORTED;
     if (N > 0 && (!st->h_pos || !st->h_vel || !st->h_goal || !st->h_attr)) return CROWDSIM_EINVAL;
     if (!st->r_pos || !st->r_vel || !st->r_goal || !st->r_attr || !st->g_time) return CROWDSIM_EINVAL;
@@ -238,7 +249,7 @@ static int launch(const crowdsim_params *prm, int B, int N, const crowdsim_state
     A.k = make_kparams(prm, N);
     if (act_only) A.k.robot_policy = CROWDSIM_ROBOT_ORCA;
     A.B = B; A.N = N; A.L = N + 1; A.EPB = envs_per_block(A.L, 128);
-    A.st = *st; A.io = *io; A.has_ep = (ep != nullptr && !act_only); A.act_only = act_only;
+    A.st = *st; A.io = *io; A.has_ep = (ep != nullptr && !act_only); A.act_only = act_only; A.n_steps = 1;
     if (A.has_ep) A.ep = *ep; else memset(&A.ep, 0, sizeof(A.ep));
     A.has_ar = (ar != nullptr && !act_only);
     if (A.has_ar) A.ar = *ar; else memset(&A.ar, 0, sizeof(A.ar));
@@ -246,34 +257,43 @@ static int launch(const crowdsim_params *prm, int B, int N, const crowdsim_state
         // small crowds: register-resident solver, 32 / (N + 1) whole envs per warp (step_flat.cuh)
         const int epb = CS_FLAT_WPB * (32 / (N + 1));
         const int blocks = (B + epb - 1) / epb;
-        // linearProgram3 queue: per warp when the launch leaves SMs mostly empty (latency-bound: no block barrier, 2-4 %
-        // faster at 1 k - 4 k envs), per block when the chip is full (issue-bound: one warp runs the pass for the whole block,
-        // 3-5 % faster at 64 k - 1 M envs). Measured with scripts/latency_probe.cu (-DCS_FLAT_WARP_LP3=0/1) and bench.py --lp3-queue.
-        static int n_sm = 0;
-        if (n_sm == 0) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148; }
-        const bool warpq = (g_lp3_queue < 0) ? (blocks * CS_FLAT_WPB <= 12 * n_sm) : (g_lp3_queue == 1);
-        #define CS_FLAT_LAUNCH(NN) do { if (warpq) step_flat_kernel<NN, 99, true><<<blocks, 32 * CS_FLAT_WPB, 0, stream>>>(A); \
-                                        else step_flat_kernel<NN, 99, false><<<blocks, 32 * CS_FLAT_WPB, 0, stream>>>(A); } while (0)
-        switch (N) {
-            case 1: CS_FLAT_LAUNCH(1); break;
-            case 2: CS_FLAT_LAUNCH(2); break;
-            case 3: CS_FLAT_LAUNCH(3); break;
-            case 4: CS_FLAT_LAUNCH(4); break;
-            default: CS_FLAT_LAUNCH(5); break;
+        const bool rot = A.k.robot_policy == CROWDSIM_ROBOT_EXTERNAL_ROT;
+        // n steps in one launch with the state in registers: closed-loop only (the robot decides on device)
+        const bool multi = n_steps > 1 && A.k.robot_policy == CROWDSIM_ROBOT_ORCA;
+        const int reps = multi ? 1 : n_steps;
+        if (multi) A.n_steps = n_steps;
+        // linearProgram3 queue of the single-step kernel: per warp when the launch leaves SMs mostly empty (latency-bound: no
+        // block barrier, 2-4 % faster at 1 k - 4 k envs), per block when the chip is full (issue-bound: one warp runs the pass
+        // for the whole block, 3-5 % faster at 64 k - 1 M envs). Measured with scripts/latency_probe.cu in round 1.
+        const bool warpq = blocks * CS_FLAT_WPB <= 12 * sm_count();
+        #define CS_FLAT_LAUNCH(NN) do { if (multi) step_flat_kernel<NN, 99, false, true, true><<<blocks, 32 * CS_FLAT_WPB, 0, stream>>>(A); \
+                                        else if (rot) step_flat_kernel<NN, 99, true, false, true><<<blocks, 32 * CS_FLAT_WPB, 0, stream>>>(A); \
+                                        else if (warpq) step_flat_kernel<NN, 99, false, false, true><<<blocks, 32 * CS_FLAT_WPB, 0, stream>>>(A); \
+                                        else step_flat_kernel<NN, 99, false, false, false><<<blocks, 32 * CS_FLAT_WPB, 0, stream>>>(A); } while (0)
+        for (int rep = 0; rep < reps; ++rep) {
+            switch (N) {
+                case 1: CS_FLAT_LAUNCH(1); break;
+                case 2: CS_FLAT_LAUNCH(2); break;
+                case 3: CS_FLAT_LAUNCH(3); break;
+                case 4: CS_FLAT_LAUNCH(4); break;
+                default: CS_FLAT_LAUNCH(5); break;
+            }
+            ++g_launches;
         }
         #undef CS_FLAT_LAUNCH
-        ++g_launches;
         return (int)cudaGetLastError();
     }
     const int threads = A.EPB * A.L;
     const int blocks = (B + A.EPB - 1) / A.EPB;
     const size_t smem = stage_bytes(A.EPB, A.L, A.k.nb_alloc, threads);
-    if (smem > 48 * 1024) {
+    if (smem > 48 * 1024) {                                  // (a per-device attribute; setting it again is cheap)
         cudaError_t err = cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return (int)err;
     }
-    step_kernel<<<blocks, threads, smem, stream>>>(A);
-    ++g_launches;
+    for (int rep = 0; rep < n_steps; ++rep) {
+        step_kernel<<<blocks, threads, smem, stream>>>(A);
+        ++g_launches;
+    }
     return (int)cudaGetLastError();
 }
 
@@ -282,14 +302,20 @@ static int launch(const crowdsim_params *prm, int B, int N, const crowdsim_state
 extern "C" int crowdsim_step(const crowdsim_params *prm, int B, int N, crowdsim_state *st, crowdsim_step_io *io,
                              crowdsim_episodes *ep, const crowdsim_autoreset *ar, void *stream)
 {
-    return cs::launch(prm, B, N, st, io, ep, ar, 0, (cudaStream_t)stream);
+    return cs::launch(prm, B, N, st, io, ep, ar, 0, 1, (cudaStream_t)stream);
+}
+
+extern "C" int crowdsim_step_n(const crowdsim_params *prm, int B, int N, crowdsim_state *st, crowdsim_step_io *io,
+                               crowdsim_episodes *ep, const crowdsim_autoreset *ar, int n_steps, void *stream)
+{
+    return cs::launch(prm, B, N, st, io, ep, ar, 0, n_steps, (cudaStream_t)stream);
 }
 
 extern "C" int crowdsim_orca_act(const crowdsim_params *prm, int B, int N, const crowdsim_state *st, double *action_out,
                                  void *stream)
 {
     crowdsim_step_io io; memset(&io, 0, sizeof(io)); io.action_out = action_out;
-    return cs::launch(prm, B, N, st, &io, nullptr, nullptr, 1, (cudaStream_t)stream);
+    return cs::launch(prm, B, N, st, &io, nullptr, nullptr, 1, 1, (cudaStream_t)stream);
 }
 
 extern "C" int crowdsim_graph_launch(void *graph_exec, void *stream, void *done_event)
@@ -307,8 +333,6 @@ extern "C" int crowdsim_event_wait(void *event)
 }
 
 extern "C" void crowdsim_debug_force_generic(int on) { cs::g_force_generic = on; }
-
-extern "C" void crowdsim_debug_lp3_queue(int mode) { cs::g_lp3_queue = mode; }
 
 extern "C" int crowdsim_abi_version(void) { return CROWDSIM_ABI_VERSION; }
 

@@ -13,6 +13,8 @@
  *                            N x Human.act -> ORCA.predict -> rvo2 doStep (crowd_sim/envs/policy/orca.py:82-132),
  *                            optionally the robot's own ORCA.predict (crowd_nav/utils/explorer.py:42), the
  *                            per-step part of Explorer.run_k_episodes (explorer.py:41-72)
+ *   crowdsim_step_n          the inner loop of Explorer.run_k_episodes for a robot that decides on device
+ *                            (crowd_nav/utils/explorer.py:41-43: robot.act -> env.step, n times), closed on the GPU
  *   crowdsim_orca_act        crowd_sim/envs/utils/robot.py:9-14 with policy ORCA (orca.py:82-132), batched
  *   crowdsim_reset           crowd_sim/envs/crowd_sim.py:251-312 + generators :155-207 (np.random MT19937)
  *   crowdsim_prefetch_scenes the same generators, run ahead of time for the NEXT episode of each env slot
@@ -37,7 +39,7 @@
 extern "C" {
 #endif
 
-#define CROWDSIM_ABI_VERSION 3
+#define CROWDSIM_ABI_VERSION 4
 
 /* error codes */
 #define CROWDSIM_OK            0
@@ -144,7 +146,9 @@ typedef struct crowdsim_episodes {
  * READY scene into the live state in the same launch (fresh episode, global_time 0, velocities 0, accumulators
  * cleared, ep_case = n_case) and marks the slot EMPTY again. If the scene is not ready yet the env is parked
  * (active = 0, want = 1) and installed by a later step; EXHAUSTED slots (case queue empty) just go inactive.
- * Single-writer protocol: only the generator moves EMPTY -> READY/EXHAUSTED, only the step kernel moves READY -> EMPTY.
+ * Single-writer protocol: only the generator moves EMPTY -> READY/EXHAUSTED, only the step kernel moves READY -> EMPTY;
+ * both sides publish with st.release.gpu and read slot data behind ld.acquire.gpu, so the generator may run concurrently
+ * with steps of the same batch on another stream.
  * Requires crowdsim_state.active != NULL.
  */
 #define CROWDSIM_SLOT_EMPTY     0
@@ -192,8 +196,6 @@ unsigned long long crowdsim_launch_count(void);
 /* Test hook: 1 = use the generic one-thread-per-agent step kernel for every N (default 0: N <= 5 uses the
  * register-resident small-crowd kernel). Both are held to the same bit-exact parity bar. */
 void crowdsim_debug_force_generic(int on);
-/* Test / tuning hook for the small-crowd kernel's linearProgram3 queue: -1 (default) = by grid size, 0 = per block, 1 = per warp. */
-void crowdsim_debug_lp3_queue(int mode);
 
 /* Host plumbing for callers that keep several env batches in flight from an interpreter (batched.HostStepper.launch /
  * wait; the reference's loop blocks in env.step, crowd_nav/utils/explorer.py:42-43): replay a captured CUDA graph
@@ -205,6 +207,19 @@ int crowdsim_event_wait(void *event);
 /* One lockstep env-step for B envs. `ep` and `ar` may be NULL. */
 int crowdsim_step(const crowdsim_params *prm, int B, int N, crowdsim_state *st, crowdsim_step_io *io,
                   crowdsim_episodes *ep, const crowdsim_autoreset *ar, void *stream);
+
+/*
+ * n_steps lockstep env-steps in one call: exactly n_steps x crowdsim_step(prm, B, N, st, io, ep, ar) -- same final state,
+ * same episode rows, same slot hand-overs; `io` holds the outputs of each env's LAST live step. With an ORCA robot
+ * (CROWDSIM_ROBOT_ORCA) nothing leaves the device between the steps of the reference's episode loop
+ * (crowd_nav/utils/explorer.py:41-43), so for N <= 5 the whole call is ONE kernel launch that keeps every env's state in
+ * registers across the steps (one load, n_steps solves, one store); an env whose episode ends installs its prefetched next
+ * scene on the spot and goes on (a second termination inside the same call finds the slot EMPTY and parks until the next
+ * crowdsim_prefetch_scenes, as n_steps single steps without a refill in between would). Other configurations
+ * (external robot actions: the same io->action every step; N > 5) run n_steps launches.
+ */
+int crowdsim_step_n(const crowdsim_params *prm, int B, int N, crowdsim_state *st, crowdsim_step_io *io,
+                    crowdsim_episodes *ep, const crowdsim_autoreset *ar, int n_steps, void *stream);
 
 /* Robot ORCA action from the current state, no mutation: action_out[B][2]. */
 int crowdsim_orca_act(const crowdsim_params *prm, int B, int N, const crowdsim_state *st, double *action_out,

@@ -387,6 +387,113 @@ def test_autoreset_device_prefetch_reproduces_suite(cuda_env, slots, suite):
     assert np.abs(frp - fr).max() < 1e-5
 
 
+@pytest.mark.parametrize('N,vis', [(5, 0), (5, 1), (4, 1), (3, 0), (2, 1), (1, 0)])
+def test_step_n_equals_n_single_steps(cuda_env, oracle, N, vis):
+    """crowdsim_step_n (one launch, state in registers across the steps) against n x oracle step on dense random scenes:
+    every state / output array equal after launches of 2, 3, 8 and 16 steps (outputs = those of the last step)."""
+    B = 1500
+    host = _random_host_state(oracle, B, N, seed=300 + N)
+    env = cuda_env(B, N, robot_visible=bool(vis), robot_policy='orca')
+    env.state.load_host(host)
+    prm = oracle.default_params(robot_visible=vis)
+    io = oracle.HostStepIO(B)
+    for n in (2, 3, 8, 16):
+        env.step_n(n)
+        for _ in range(n):
+            oracle.step(prm, host, io)
+        torch.cuda.synchronize()
+        _assert_state_equal(env, host, what='step_n N=%d n=%d' % (N, n))
+        _assert_io_equal(env, io, what='step_n N=%d n=%d' % (N, n))
+
+
+@pytest.mark.parametrize('name', ['circle5_invisible', 'circle5_visible', 'square5_invisible', 'mixed5_invisible'])
+def test_step_n_full_suites_from_reference_scenes(cuda_env, oracle, name):
+    """Whole reference episodes through crowdsim_step_n with episode bookkeeping (envs freeze when their episode ends,
+    inside the launch): result rows identical to the reference's Python for every test case."""
+    N, rule, vis, rand = SUITES[name]
+    cases = load_golden('suite_' + name)['cases']
+    B = len(cases)
+    host = fill_host_state(oracle, [c['init'] for c in cases], N)
+    env = cuda_env(B, N, rule, robot_visible=bool(vis))
+    ep = env.track_episodes(B)
+    env.state.load_host(host)
+    ep.ep_case.copy_(torch.arange(B, dtype=torch.int32))
+    for n in (1, 2, 5, 16, 16, 16, 16, 16, 16, 16):
+        env.step_n(n)
+    torch.cuda.synchronize()
+    assert int(env.state.active.sum()) == 0
+    info = ep.res_info.cpu().numpy(); steps = ep.res_steps.cpu().numpy(); t = ep.res_time.cpu().numpy()
+    ret = ep.res_return.cpu().numpy(); tc = ep.res_too_close.cpu().numpy(); mds = ep.res_min_dist_sum.cpu().numpy()
+    frp = ep.res_final_rpos.cpu().numpy(); hp = env.state.h_pos.cpu().numpy()
+    for i, c in enumerate(cases):
+        assert info[i] == c['info'] and steps[i] == c['steps'], (name, c['case'])
+        assert t[i] == (25.0 if c['info'] == 4 else float(c['global_time']))
+        assert ret[i] == float(c['return']) and tc[i] == c['too_close'] and mds[i] == float(c['min_dist_sum'])
+        r, h = scene_arrays(c['final'], N)
+        assert (frp[i] == r[:2]).all() and (hp[i] == h[:, :2]).all()
+
+
+@pytest.mark.parametrize('N,n', [(5, 4), (5, 7), (3, 5)])
+def test_step_n_autoreset_bit_exact(cuda_env, oracle, N, n):
+    """crowdsim_step_n with the auto-reset protocol: scenes prefetched by the oracle before every launch, installed inside
+    the launch when an episode ends (a second termination in the same launch parks), result rows, slot flags and the whole
+    state equal to n x oracle step through hundreds of episode boundaries and the exhaustion of the case queue."""
+    B, k = 96, 600
+    prm = oracle.default_params()
+    host = oracle.HostState(B, N); io = oracle.HostStepIO(B); hep = oracle.HostEpisodes(B, k); har = oracle.HostAutoReset(B, N)
+    counter = np.zeros(1, dtype=np.int32)
+    q = dict(case_counter=counter, case_total=k, seed_base=2000)
+    oracle.reset(host, None, ep=hep, **q)
+    env = cuda_env(B, N)
+    ep = env.track_episodes(k)
+    env.enable_autoreset()
+    env.state.load_host(host)
+    ep.ep_case.copy_(torch.from_numpy(hep.ep_case))
+    it = 0
+    while (host.active.any() or har.want.any()) and it < 1500:
+        if it % 2 == 0:                                      # no refill before every other launch: more envs park
+            oracle.prefetch(har, B, N, **q)
+        env.autoreset.load_host(har)
+        env.step_n(n)
+        for _ in range(n):
+            oracle.step(prm, host, io, hep, har)
+        torch.cuda.synchronize()
+        d = env.autoreset.to_host()
+        assert np.array_equal(d['n_state'], har.n_state) and np.array_equal(d['want'], har.want), it
+        assert np.array_equal(env.state.active.cpu().numpy(), host.active), it
+        if it % 10 == 0:
+            _assert_state_equal(env, host, what='step_n autoreset N=%d it=%d' % (N, it))
+            for f in ('ep_case', 'ep_steps', 'ep_return', 'ep_too_close', 'ep_min_dist_sum'):
+                assert np.array_equal(getattr(ep, f).cpu().numpy(), getattr(hep, f)), (f, it)
+        it += 1
+    assert int(counter[0]) >= k
+    _assert_state_equal(env, host, what='step_n autoreset final')
+    _assert_io_equal(env, io, what='step_n autoreset final')
+    for f in ('res_info', 'res_steps', 'res_time', 'res_return', 'res_too_close', 'res_min_dist_sum', 'res_final_rpos'):
+        assert np.array_equal(getattr(ep, f).cpu().numpy(), getattr(hep, f)), f
+
+
+def test_step_n_generic_and_external_fall_back_to_launch_loops(cuda_env, oracle):
+    """n_steps > 1 outside the register-resident case (N > 5; external robot action, applied on every step) = n launches
+    of the single-step kernels: same results as n oracle steps."""
+    for N, policy in ((8, 'orca'), (5, 'external_xy')):
+        from crowdnav_b200 import _abi
+        B = 400
+        host = _random_host_state(oracle, B, N, seed=77 + N)
+        env = cuda_env(B, N, robot_policy=policy)
+        env.state.load_host(host)
+        prm = oracle.default_params(robot_policy=_abi.ROBOT_ORCA if policy == 'orca' else _abi.ROBOT_EXTERNAL_XY)
+        io = oracle.HostStepIO(B)
+        io.action[...] = np.random.RandomState(2).uniform(-1, 1, (B, 2))
+        act = torch.from_numpy(io.action).to(env.device)
+        env.step(None if policy == 'orca' else act, n_steps=5)
+        for _ in range(5):
+            oracle.step(prm, host, io)
+        torch.cuda.synchronize()
+        _assert_state_equal(env, host, what='step_n fallback N=%d' % N)
+        _assert_io_equal(env, io, what='step_n fallback N=%d' % N)
+
+
 def test_lookahead_humans_matches_oracle(cuda_env, oracle):
     """crowdsim_lookahead_humans = the `ob` of env.onestep_lookahead (crowd_sim.py:414-416): bit-exact against one oracle
     step on a copy of the state, small and large crowds, robot visible or not; the live state is untouched."""
