@@ -48,8 +48,9 @@ def parse():
     ap.add_argument('--pools', type=int, default=0, help='independent batches rotated through (0 = enough to exceed L2)')
     ap.add_argument('--rule', default='circle_crossing')
     ap.add_argument('--streams', type=int, default=16, help='independent env batches stepped concurrently (CUDA streams inside the timed graph)')
-    ap.add_argument('--prefetch-every', type=int, default=4, help='scene-prefetch launch for a batch on every n-th visit of that batch')
     ap.add_argument('--e2e-batches', type=int, default=16, help='independent env batches kept in flight by the e2e leg')
+    ap.add_argument('--e2e-obs', default='f32', choices=['f32', 'f64'], help='observation format of the e2e leg (HostStepper obs=)')
+    ap.add_argument('--chunk', type=int, default=8, help='env-steps per launch (crowdsim_step_n); 1 = one launch per step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-python-loop', action='store_true', help='reference arm: skip the reference-shaped Python loop timing')
     ap.add_argument('--no-scale', action='store_true', help='skip the supplementary 1 Mi-env launch measurement')
@@ -125,58 +126,77 @@ class ClockSampler(object):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-def pick_threads(po, args):
-    """'All the host threads it can use': each thread owns a fixed range of the batch's envs inside one parallel region
-    (oracle.run_passes); SMT oversubscription or a busy host can still make fewer threads faster, so calibrate: time short
-    runs at cpu_count, /2, /4, ... and keep the best."""
-    import numpy as np
-    B, N = args.envs, args.humans
-    prm = po.default_params()
-    st = po.HostState(B, N); io = po.HostStepIO(B)
-    seeds = (np.arange(B) + 2000).astype(np.uint32)
-    po.reset(st, seeds, args.rule, seed_stride=B)
-    best = (0.0, 1)
-    n = os.cpu_count() or 1
-    cands = sorted({max(1, n >> s) for s in range(0, 6)}, reverse=True)
-    for th in cands:
-        po.set_threads(th)
-        po.run_passes(prm, st, io, seeds, 10, args.rule, seed_stride=B)
-        rate = 0.0
-        for _ in range(3):                               # best of 3 short trials (>= 60 ms each) per thread count
-            t0 = time.perf_counter(); done = 0
-            while time.perf_counter() - t0 < 0.06:
-                po.run_passes(prm, st, io, seeds, 20, args.rule, seed_stride=B); done += 20
-            rate = max(rate, done * B / (time.perf_counter() - t0))
-            if rate < 0.25 * best[0]:                    # hopeless thread count (oversubscribed / spinning): do not retry it
-                break
-        if rate > best[0]:
-            best = (rate, th)
-    po.set_threads(best[1])
-    return best[1]
+def usable_cpus():
+    """Logical CPUs this process may run on (cgroup / affinity mask aware), not os.cpu_count()."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
 
 
-def cpu_oracle_rate(args, seconds=12.0):
-    """Oracle port (plain C restatement of the reference loop) on the host cores, same workload definition:
-    lockstep passes over a 4096-env batch with auto-reset. Returns (env-steps/s, threads, sample description)."""
-    import numpy as np
-    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
-    import pyoracle as po
-    nthreads = pick_threads(po, args)
-    B, N = args.envs, args.humans
-    prm = po.default_params()
-    st = po.HostState(B, N); io = po.HostStepIO(B)
-    seeds = (np.arange(B) + 2000).astype(np.uint32)
-    po.reset(st, seeds, args.rule, seed_stride=B)
-    po.run_passes(prm, st, io, seeds, 50, args.rule, seed_stride=B)
-    rates, n_total, t_begin = [], 0, time.perf_counter()
-    for _ in range(5):                                   # median of 5 segments: the host is shared, single segments are noisy
+class CpuArm(object):
+    """The CPU arm: the C restatement of the reference loop (oracle/crowdsim_oracle.c), one batch of `envs` envs stepped in
+    lockstep inside ONE OpenMP parallel region (every thread owns a fixed range of envs, one barrier per pass, finished envs
+    are re-seeded in place). 'All the host threads it can use' is calibrated, because a barrier per 270 us pass collapses
+    when the region is oversubscribed: every candidate thread count (usable CPUs, /2, /4, ...) is timed over windows of
+    >= 0.4 s and the best median wins; the timed run is then checked against the calibrated rate."""
+
+    def __init__(self, args):
+        import numpy as np
+        sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+        os.environ.setdefault('OMP_WAIT_POLICY', 'passive')      # before libgomp starts: spinning waiters make oversubscription fatal
+        os.environ.setdefault('OMP_PROC_BIND', 'false')
+        import pyoracle as po
+        self.po, self.np, self.args = po, np, args
+        self.B, self.N = args.envs, args.humans
+        self.prm = po.default_params()
+        self.st = po.HostState(self.B, self.N); self.io = po.HostStepIO(self.B)
+        self.seeds = (np.arange(self.B) + 2000).astype(np.uint32)
+        po.reset(self.st, self.seeds, args.rule, seed_stride=self.B)
+        self.passes(60)                                          # into steady state (episodes at all phases)
+        self.calibration = {}
+
+    def passes(self, n):
+        self.po.run_passes(self.prm, self.st, self.io, self.seeds, n, self.args.rule, seed_stride=self.B)
+
+    def rate(self, seconds, block=20):
+        """env-steps/s over a window of >= `seconds`."""
         t0 = time.perf_counter(); n = 0
-        while time.perf_counter() - t0 < seconds / 5:
-            po.run_passes(prm, st, io, seeds, 100, args.rule, seed_stride=B); n += 100
-        rates.append(B * n / (time.perf_counter() - t0)); n_total += n
-    rates.sort()
-    return rates[2], nthreads, '%d lockstep passes over a %d-env batch (auto-reset) inside one OpenMP region, %.1f s, median of 5 segments (min %.2e, max %.2e)' % (
-        n_total, B, time.perf_counter() - t_begin, rates[0], rates[-1])
+        while time.perf_counter() - t0 < seconds:
+            self.passes(block); n += block
+        return n * self.B / (time.perf_counter() - t0)
+
+    def calibrate(self):
+        n = usable_cpus()
+        cands = sorted({max(1, n >> s) for s in range(0, 6)}, reverse=True)
+        best = (0.0, 1)
+        for th in cands:
+            self.po.set_threads(th)
+            self.passes(5)
+            r = sorted(self.rate(0.4) for _ in range(3))[1]      # median of three 0.4 s windows
+            self.calibration[th] = r
+            if r > best[0]:
+                best = (r, th)
+            if r < 0.5 * best[0] and th < best[1]:               # past the optimum: fewer threads only get slower
+                break
+        self.threads, self.calibrated_rate = best[1], best[0]
+        self.po.set_threads(self.threads)
+        return self.threads
+
+    def timed(self, steps, warmup, min_seconds=1.0):
+        """`steps` lockstep passes per replay, replays back to back for >= min_seconds: returns (median replay seconds,
+        replays, min, max). If the run falls below half the calibrated rate (the host got busy), calibrate again once."""
+        for attempt in range(2):
+            self.passes(max(warmup, 3))
+            ts = []
+            t_begin = time.perf_counter()
+            while (time.perf_counter() - t_begin < min_seconds or len(ts) < 5) and len(ts) < 20000:
+                t0 = time.perf_counter(); self.passes(steps); ts.append(time.perf_counter() - t0)
+            ts.sort()
+            med = ts[len(ts) // 2]
+            if self.B * steps / med >= 0.5 * self.calibrated_rate or attempt == 1:
+                return med, len(ts), ts[0], ts[-1], attempt
+            self.calibrate()
 
 
 WORKLOAD = '%d batched envs x %d ORCA humans, %s, ORCA robot (invisible), auto-reset, per GPU'
@@ -188,21 +208,12 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    import numpy as np
-    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
-    import pyoracle as po
+    arm = CpuArm(args)
+    cores = arm.calibrate()
     B, N = args.envs, args.humans
-    cores = pick_threads(po, args)
-    prm = po.default_params()
-    st = po.HostState(B, N); io = po.HostStepIO(B)
-    seeds = (np.arange(B) + 2000).astype(np.uint32)
-    po.reset(st, seeds, args.rule, seed_stride=B)
-
-    po.run_passes(prm, st, io, seeds, args.warmup, args.rule, seed_stride=B)
-    t0 = time.perf_counter()
-    po.run_passes(prm, st, io, seeds, args.steps, args.rule, seed_stride=B)     # all passes inside one OpenMP parallel region
-    dt = time.perf_counter() - t0
-    v = B * args.steps / dt
+    med, replays, tmin, tmax, recal = arm.timed(args.steps, args.warmup, min_seconds=2.0)
+    v = B * args.steps / med
+    po, prm, st, io, seeds = arm.po, arm.prm, arm.st, arm.io, arm.seeds
     # the same port driven one call per pass from the interpreter (step; reset of the finished envs), like a host loop would
     t1 = time.perf_counter(); n_calls = 0
     while time.perf_counter() - t1 < 1.0:
@@ -215,27 +226,43 @@ def run_reference(args):
     py = None
     if not args.no_python_loop:
         import pyloop
+        procs = min(usable_cpus(), 64)
         one, n1 = pyloop.timed_rate(list(range(1000, 1064)), N, args.rule)
-        allc, n2, procs = pyloop.timed_rate_all_cores(list(range(1000, 1000 + 16 * min(os.cpu_count() or 1, 64))), N, args.rule,
-                                                      procs=min(os.cpu_count() or 1, 64))
+        allc, n2, procs = pyloop.timed_rate_all_cores(list(range(1000, 1000 + 16 * procs)), N, args.rule, procs=procs)
         py = {'one_core_env_steps_per_s': one, 'all_cores_env_steps_per_s': allc, 'processes': procs,
               'sample': '%d + %d env-steps of the seeded test cases; Python loop + C rvo2 shim (oracle/pyloop.py); the reference\'s '
                         'own Python measured 4.8 k env-steps/s/core in the build container (DESIGN.md 6)' % (n1, n2)}
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'env-steps/s', 'n_gpus': args.gpus, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'warmup': args.warmup, 'ms_per_step': 1e3 * med / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f64 state + f32 ORCA solver', 'data': 'synthetic',
             'config': {'workload': WORKLOAD % (B, N, args.rule), 'envs_per_gpu': B, 'humans': N,
-                       'note': 'CPU arm: one 4096-env batch stepped in lockstep by all host threads (rank 0 only)'},
+                       'note': 'CPU arm: one %d-env batch stepped in lockstep by all host threads (rank 0 only)' % B},
             'cpu_baseline': {'value': v, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
-                             'sample': '%d lockstep passes over a %d-env batch in one C call; C restatement of the reference loop '
-                                       '(oracle/crowdsim_oracle.c, OpenMP: every thread owns a range of envs, thread count calibrated, host has %d logical CPUs)' % (args.steps, B, os.cpu_count() or 0),
-                             'per_pass_calls_value': per_call},
+                             'sample': 'median of %d back-to-back replays of %d lockstep passes over a %d-env batch (one C call per replay, min %.3g s, max %.3g s); '
+                                       'C restatement of the reference loop (oracle/crowdsim_oracle.c, OpenMP: every thread owns a range of envs; '
+                                       'thread count calibrated over %s usable CPUs)' % (replays, args.steps, B, tmin, tmax, usable_cpus()),
+                             'calibration_env_steps_per_s': {str(k): arm.calibration[k] for k in sorted(arm.calibration)},
+                             'recalibrated': bool(recal), 'per_pass_calls_value': per_call},
             'e2e': {'value': v, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'python_loop': py, 'gpu_launches': 0}
     print(json.dumps(line))
 
 
+def cpu_oracle_rate(args, seconds=10.0):
+    """cpu_baseline leg of the default run: same arm, `seconds` of CPU work."""
+    arm = CpuArm(args)
+    cores = arm.calibrate()
+    rates = sorted(arm.rate(seconds / 5, block=50) for _ in range(5))
+    return rates[2], cores, 'lockstep passes over a %d-env batch (auto-reset) inside one OpenMP region, %.0f s, median of 5 segments (min %.2e, max %.2e); threads calibrated over %d usable CPUs' % (
+        args.envs, seconds, rates[0], rates[-1], usable_cpus())
+
+
 # ----------------------------------------------------------------------------------------------------------------------
+def _lcm(a, b):
+    import math
+    return a * b // math.gcd(a, b)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -251,9 +278,26 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=dev)
     sampler = ClockSampler(local)                            # started early: its start-up must be over before the timed region
     lib = _abi.load()
-    B, N, K, W = args.envs, args.humans, args.steps, args.warmup
+    B, N, K, W, C = args.envs, args.humans, args.steps, args.warmup, max(1, args.chunk)
     bytes_per_env = ALG_BYTES(N)
     pools = args.pools or max(2, int(1.3 * 126e6 / (B * bytes_per_env)) + 1)
+    S = max(1, min(args.streams, pools))
+    pools = (pools + S - 1) // S * S                         # every stream owns the same number of batches
+    round_steps = pools * C                                  # bench steps of one round (every batch advanced by C steps)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- how many steps get timed: R back-to-back replays of K steps, no gap between them (the streams are only joined
+    # at the two ends of the region), R >= 200 for short K and long enough for >= ~80 ms; whole rounds only ----
+    est_us_per_step = 2.0
+    unit = _lcm(K, round_steps)
+    want_steps = max(200 * K if K <= 4096 else K, int(0.08 / (est_us_per_step * 1e-6)))
+    timed_steps = min((want_steps + unit - 1) // unit * unit, max(unit, 4_000_000 // unit * unit))
+    rounds = timed_steps // round_steps
+    warm_rounds = max(24, (max(W, 3) + round_steps - 1) // round_steps)     # >= 24 x C = 192 steps per batch: steady episode mix
 
     envs = []
     for p in range(pools):
@@ -262,8 +306,8 @@ def run_ours(args):
         env.set_robot_policy('orca')
         # every batch streams its own range of train-phase cases (seed = 2000 + case, crowd_sim.py:272-273) through its
         # B slots; per-episode result rows are recorded on device and reduced once at the end (the path's one collective)
-        visits = (max(W, 3) + K + 3) // pools + 2
-        env.k_total = B * (visits // 5 + 3)
+        visits = (warm_rounds + rounds + 8) * C + 600 + (8000 if p < max(1, args.e2e_batches) else 0)   # the first batches also serve the single-batch and e2e legs
+        env.k_total = B * (visits // 6 + 4)                  # episodes last >= 7 steps
         env.track_episodes(env.k_total, gamma=0.9)
         env.set_case_queue((rank * pools + p) * env.k_total, env.k_total, 'train')
         env.enable_autoreset(args.rule)
@@ -272,85 +316,87 @@ def run_ours(args):
         envs.append(env)
     torch.cuda.synchronize()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # One bench step = the fused step kernel on the main stream (it also installs the prefetched next scene of every env
-    # whose episode just ended) + one scene-prefetch kernel for that batch on a side stream (off the critical path: it
-    # only has to finish before the same batch is stepped again). The whole timed region is ONE CUDA graph of K steps:
-    # Python/ctypes launch overhead (~20 us per call) would otherwise dominate a 4096-env step.
+    # ---- one CUDA graph per stream: for each batch the stream owns, C closed-loop env-steps in ONE launch (crowdsim_step_n:
+    # state in registers, finished envs install their prefetched next scene inside the launch) and, on the stream's side
+    # stream, the refill of the consumed next-scene slots (it may overlap later launches: release/acquire slot hand-over).
+    # The streams never wait for each other: batch p always runs on stream p mod S, a round = every stream replays its graph
+    # once; Python only issues S raw graph launches per round (crowdsim_graph_launch, ~3 us each) and stays ahead. ----
     main = torch.cuda.Stream(device=dev)
-    LANES = max(1, min(args.streams, pools))
-    lanes = [torch.cuda.Stream(device=dev) for _ in range(LANES)]
-    sides = [torch.cuda.Stream(device=dev) for _ in range(max(4, LANES))]
-    it = 0
-    n_prefetch = 0
+    lanes = [torch.cuda.Stream(device=dev) for _ in range(S)]
+    sides = [torch.cuda.Stream(device=dev) for _ in range(S)]
 
-    def capture(n_steps, with_prefetch=True, step_fn=None, n_lanes=None):
-        """One CUDA graph of n_steps bench steps. Batch p is always stepped on lane (stream) p % n_lanes: the steps of one
-        batch stay ordered, steps of different (independent) batches may overlap on the device when n_lanes > 1."""
-        nonlocal it, n_prefetch
-        n_prefetch = 0
-        n_lanes = n_lanes or LANES
+    def stream_graph(s, batch_ids, n_chunks=1, step_fn=None, side=False):
+        """A graph that is a plain sequence of launches on ONE stream (no fork / join): lane graphs step, side graphs refill."""
         g = torch.cuda.CUDAGraph()
-        pending = {}                                   # pool -> event of its last prefetch inside this capture
-        with torch.cuda.graph(g, stream=main):
-            fork = torch.cuda.Event(); fork.record(main)
-            for ls in lanes[:n_lanes]:
-                ls.wait_event(fork)
-            for _ in range(n_steps):
-                p = it % pools; env = envs[p]; it += 1
-                ls = lanes[p % n_lanes]
-                with torch.cuda.stream(ls):
-                    if p in pending:
-                        ls.wait_event(pending.pop(p))
-                    (step_fn or (lambda e: e.step()))(env)
-                    if with_prefetch and ((it - 1) // pools) % args.prefetch_every == 0:
-                        n_prefetch += 1
-                        ev = torch.cuda.Event(); ev.record(ls)
-                        sd = sides[p % len(sides)]
-                        sd.wait_event(ev)
-                        with torch.cuda.stream(sd):
-                            env.prefetch()
-                            done = torch.cuda.Event(); done.record(sd)
-                        pending[p] = done
-            for ev in pending.values():                # join the side branches and the lanes
-                main.wait_event(ev)
-            for ls in lanes[:n_lanes]:
-                ev = torch.cuda.Event(); ev.record(ls); main.wait_event(ev)
+        st_ = sides[s] if side else lanes[s]
+        with torch.cuda.graph(g, stream=st_):
+            for _ in range(n_chunks):
+                for p in batch_ids:
+                    (step_fn or (lambda e: e.step_n(C) if C > 1 else e.step()))(envs[p])
         return g
-    with torch.cuda.stream(main):
-        for _ in range(3):
-            envs[it % pools].step(); envs[it % pools].prefetch(); it += 1
+    for s in range(S):                                       # lazy initialisations outside capture
+        with torch.cuda.stream(lanes[s]):
+            envs[s].step(); envs[s].prefetch()
     torch.cuda.synchronize()
-    g_warm = capture(max(W, 3))
-    g_timed = capture(K)
-    timed_prefetches = n_prefetch
+    refill = lambda e: e.prefetch()  # noqa: E731
+    graphs = [stream_graph(s, list(range(s, pools, S))) for s in range(S)]
+    fills = [stream_graph(s, list(range(s, pools, S)), step_fn=refill, side=True) for s in range(S)]
+    # a round = every lane replays its step graph, every side stream its refill graph. The refills are NOT ordered against
+    # the steps (the generator fills whatever slots it finds EMPTY, the step kernel installs whatever it finds READY:
+    # release / acquire hand-over per slot), so no stream ever waits for another one.
+    execs = [(g.raw_cuda_graph_exec(), lanes[s].cuda_stream) for s, g in enumerate(graphs)] + \
+            [(g.raw_cuda_graph_exec(), sides[s].cuda_stream) for s, g in enumerate(fills)]
+    launches_per_round = 2 * pools
 
-    def env_steps_done():
+    def run_rounds(n, tick=None):
+        """n rounds on all streams between two events on `main` (returns them); tick: list that receives one event per round
+        recorded on stream 0."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main)
+        for ls in lanes + sides:
+            ls.wait_event(e0)
+        for r in range(n):
+            for ex, sh in execs:
+                rc = lib.crowdsim_graph_launch(ex, sh, None)
+                if rc:
+                    _abi.check(rc, 'crowdsim_graph_launch')
+            if tick is not None:
+                ev = torch.cuda.Event(enable_timing=True); ev.record(lanes[0]); tick.append(ev)
+        for ls in lanes + sides:
+            ev = torch.cuda.Event(); ev.record(ls); main.wait_event(ev)
+        e1.record(main)
+        return e0, e1
+
+    def env_steps_done(which=None):
         """env-steps actually performed so far on this rank (finished episodes + episodes in progress): an env whose next
         scene is not ready when its episode ends is parked until the refill arrives and performs no env-step meanwhile."""
         tot = 0
-        for env in envs:
+        for env in (envs if which is None else which):
             n = int(min(env._case_counter.item(), env.k_total))
             tot += int(env.episodes.res_steps[:n].sum().item()) + int((env.episodes.ep_steps * env.state.active.to(torch.int32)).sum().item())
         return tot
-    with torch.cuda.stream(main):
-        g_warm.replay()
+
+    # ---- warm-up: every batch far into steady state (>= 192 steps, i.e. several episode lengths: the mix of episode phases is
+    # stationary), then a few timed rounds to size the region ----
+    run_rounds(warm_rounds)
+    torch.cuda.synchronize()
+    a0, a1 = run_rounds(4)
+    torch.cuda.synchronize()
+    est_us_per_step = 1e3 * a0.elapsed_time(a1) / (4 * round_steps)
+    want_steps = max(200 * K if K <= 4096 else K, int(0.08 / (est_us_per_step * 1e-6)))
+    timed_steps = min((want_steps + unit - 1) // unit * unit, rounds * round_steps)
+    rounds = timed_steps // round_steps
+    warm_done = (warm_rounds + 4) * round_steps
+
     barrier()
     steps_before = env_steps_done()
     sampler.wait_ready()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ticks = []
     sampler.mark_start()
-    with torch.cuda.stream(main):
-        e0.record()
-        g_timed.replay()
-        e1.record()
+    e0, e1 = run_rounds(rounds, tick=ticks)
     barrier()
     sampler.mark_stop()
-    launches = K + timed_prefetches
+    launches = rounds * launches_per_round
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
     live_steps = env_steps_done() - steps_before             # counted on device by the step kernel itself
@@ -361,7 +407,15 @@ def run_ours(args):
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     ms_max = float(t.item())
     live_total = int(cnt.item())
-    value = live_total / (ms_max * 1e-3)                     # == world * B * K / time unless envs were parked
+    value = live_total / (ms_max * 1e-3)                     # == world * B * timed_steps / time unless envs were parked
+    # distribution over the rounds (stream 0's clock): a steady region has median ~ mean
+    rt = sorted(ticks[i].elapsed_time(ticks[i + 1]) for i in range(len(ticks) - 1)) if len(ticks) > 2 else []
+    round_stats = None
+    if rt:
+        med = rt[len(rt) // 2]
+        round_stats = {'rounds': rounds, 'steps_per_round': round_steps, 'median_ms': med, 'p10_ms': rt[len(rt) // 10], 'p90_ms': rt[(9 * len(rt)) // 10],
+                       'median_value': world * B * round_steps / (med * 1e-3),
+                       'note': 'per-round durations on stream 0 of rank 0 (every batch advanced by %d steps per round); median_value = nominal env-steps of a round / median' % C}
 
     # ---- the path's single collective: gather of episode statistics (terminal-class counts + env-steps of all finished
     # episodes of every rank) to rank 0 ----
@@ -386,61 +440,92 @@ def run_ours(args):
                 'note': 'all episodes finished so far on all ranks (gathered with one NCCL all_gather when n_gpus > 1); reference '
                         '500-case test suite: 0.43 / 0.57 / 0.006'}
 
-    # ---- the same bench step with ONE batch in flight (every step launch waits for the previous one): reported next to
-    # `value`, which keeps `--streams` independent batches in flight ----
-    single = None
-    if LANES > 1:
-        Ks = max(pools, K // 4)
-        g_single = capture(Ks, n_lanes=1)
-        barrier()
+    # ---- BASELINE config 2 taken literally: ONE batch of 4096 envs, nothing else on the GPU. (a) the same batch over and
+    # over (its 2.6 MB of state stay in L2 -- and, inside a launch, in registers); (b) one batch in flight at a time but
+    # rotating through all batches, so every launch reads its state from HBM. Auto-reset and scene refill included. ----
+    def time_pair(g_step, g_fill, reps):
+        """reps x (step graph on lane 0 || refill graph on side 0), CUDA events on lane 0 (the refills overlap the steps)."""
         q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(main):
-            q0.record(); g_single.replay(); q1.record()
+        barrier()
+        sides[0].wait_stream(lanes[0])
+        with torch.cuda.stream(lanes[0]):
+            q0.record()
+        for _ in range(reps):
+            with torch.cuda.stream(lanes[0]):
+                g_step.replay()
+            with torch.cuda.stream(sides[0]):
+                g_fill.replay()
+        with torch.cuda.stream(lanes[0]):
+            q1.record()
         barrier()
         tq = torch.tensor([q0.elapsed_time(q1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tq, op=dist.ReduceOp.MAX)
-        single = {'value': world * B * Ks / (float(tq.item()) * 1e-3), 'unit': 'env-steps/s', 'steps': Ks, 'ms_per_step': float(tq.item()) / Ks,
-                  'note': 'one 4096-env batch in flight at a time (single stream), nominal env-step count'}
-        del g_single
+        return float(tq.item())
+    n_ch = 4
+    one = [envs[0]]
+    g_same, f_same = stream_graph(0, [0], n_chunks=n_ch), stream_graph(0, [0], step_fn=refill, side=True)
+    reps = max(3, int(0.03 / (n_ch * C * 8e-6)))
+    time_pair(g_same, f_same, 2)
+    b0 = env_steps_done(one)
+    ms_same = time_pair(g_same, f_same, reps)
+    done_same = env_steps_done(one) - b0
+    g_rot, f_rot = stream_graph(0, list(range(pools))), stream_graph(0, list(range(pools)), step_fn=refill, side=True)
+    time_pair(g_rot, f_rot, 1)
+    b1 = env_steps_done()
+    ms_rot = time_pair(g_rot, f_rot, 3)
+    done_rot = env_steps_done() - b1
+    single = {'value': world * done_same / (ms_same * 1e-3), 'unit': 'env-steps/s',
+              'us_per_step': 1e3 * ms_same / (reps * n_ch * C),
+              'rotating_value': world * done_rot / (ms_rot * 1e-3), 'rotating_us_per_step': 1e3 * ms_rot / (3 * pools * C),
+              'note': 'config-literal: ONE %d-env batch in flight. value: the same batch stepped %d x %d steps back to back (state L2-resident between '
+                      'launches); rotating_value: one batch in flight, rotating over %d batches (state from HBM). Both with auto-reset + scene refill '
+                      '(side stream); env-steps counted by the kernel' % (B, reps * n_ch, C, pools)}
+    del g_same, g_rot, f_same, f_rot
 
-    # ---- roofline of the dominant kernel (the step kernel): a graph of one step launch per pool, no resets in between,
-    # replayed R times; CUDA events on the launching stream; per-launch duration = elapsed / (R * pools). The pools
-    # rotate, so each launch reads its state from HBM, not L2. ----
-    def step_only(env):
-        ep, ar = env.episodes, env.autoreset         # no bookkeeping / auto-reset: finished envs keep stepping (same work)
-        env.episodes = None; env.autoreset = None
-        env.step()
-        env.episodes, env.autoreset = ep, ar
-    g_step = capture(pools, with_prefetch=False, step_fn=step_only, n_lanes=1)
-    with torch.cuda.stream(main):
-        g_step.replay()
-    torch.cuda.synchronize()
-    R = max(3, min(20, 1200 // pools))
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(main):
-        k0.record()
-        for _ in range(R):
-            g_step.replay()
-        k1.record()
-    torch.cuda.synchronize()
-    k_avg = k0.elapsed_time(k1) / (R * pools)
+    # ---- roofline of the dominant kernel (the step kernel of the timed region: crowdsim_step_n with C steps per launch): a
+    # single-stream graph of one launch per batch, no bookkeeping / resets in between, replayed R times; CUDA events on the
+    # launching stream; per-launch duration = elapsed / (R * pools). The batches rotate: each launch reads its state from HBM.
+    # Algorithmic bytes per launch = C steps x B envs x 634 B (SURVEY.md 8d: the per-env-step figure x the env-steps a launch
+    # performs); the launch's actual DRAM traffic is lower -- that is the point of keeping the state in registers. ----
+    def kernel_us(n):
+        """Average duration of one step launch (n env-steps) in the bench's own steady state: episode bookkeeping and
+        auto-reset ON (finished envs install their next scene and go on -- without resets every episode would run out into
+        a quiet scene, the cheapest input there is), the scene refills run between the timed replays, untimed."""
+        g_fill = stream_graph(0, list(range(pools)), step_fn=refill)
+        g_k = stream_graph(0, list(range(pools)), step_fn=(lambda e: e.step_n(n)) if n > 1 else (lambda e: e.step()))
+        tot = 0.0
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for r in range(R + 1):
+            with torch.cuda.stream(lanes[0]):
+                g_fill.replay()
+                q0.record(); g_k.replay(); q1.record()
+            torch.cuda.synchronize()
+            if r > 0:
+                tot += q0.elapsed_time(q1)
+        return tot / (R * pools)
     peak, peak_src = load_peaks()
-    achieved = B * bytes_per_env / (k_avg * 1e-3) / 1e9
+    R = max(3, min(20, 1200 // pools))
+    k_avg = kernel_us(C)
+    k1_avg = kernel_us(1) if C > 1 else k_avg
+    achieved = C * B * bytes_per_env / (k_avg * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'step_traffic.json')
     if os.path.exists(tpath) and N == 5 and B == 4096:
         tj = json.load(open(tpath))
-        traffic = tj['dram_bytes_read'] + tj['dram_bytes_write']          # from the committed ncu --set full capture, per launch
-    roofline = {'bound': 'hbm', 'kernel': 'cs::step_flat_kernel' if N <= 5 else 'cs::step_kernel', 'achieved': achieved, 'peak': peak,
-                'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
-                'algorithmic_bytes_per_launch': B * bytes_per_env, 'avg_launch_us': 1e3 * k_avg,
-                'how': 'CUDA events around %d replays of a single-stream graph of %d back-to-back step launches (one per rotating batch)' % (R, pools),
+        if tj.get('steps_per_launch', 1) == C:
+            traffic = tj['dram_bytes_read'] + tj['dram_bytes_write']      # from the committed ncu --set full capture, per launch
+    roofline = {'bound': 'hbm', 'kernel': ('cs::step_flat_kernel<%d, MULTI> (crowdsim_step_n, %d env-steps per launch)' % (N, C)) if N <= 5 and C > 1 else ('cs::step_flat_kernel' if N <= 5 else 'cs::step_kernel'),
+                'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': C * B * bytes_per_env, 'avg_launch_us': 1e3 * k_avg, 'env_steps_per_launch': C * B,
+                'how': 'CUDA events around each of %d replays of a single-stream graph of %d back-to-back step launches (one per rotating batch, bookkeeping + auto-reset on, scene refills between the replays untimed)' % (R, pools),
+                'single_step_kernel': {'avg_launch_us': 1e3 * k1_avg, 'achieved': B * bytes_per_env / (k1_avg * 1e-3) / 1e9,
+                                       'frac': B * bytes_per_env / (k1_avg * 1e-3) / 1e9 / peak, 'note': 'crowdsim_step (one env-step per launch), same measurement; round 1: 0.039'},
                 'timed_region_GBps': (live_total / world) * bytes_per_env / (ms_max * 1e-3) / 1e9,
                 'timed_region_frac': (live_total / world) * bytes_per_env / (ms_max * 1e-3) / 1e9 / peak,
-                'timed_region_note': 'algorithmic bytes of all steps of the timed region / its duration, with %d independent batches in flight' % LANES}
+                'timed_region_note': 'algorithmic bytes of all steps of the timed region / its duration, with %d independent batches in flight' % S}
 
-    # ---- supplementary: the same step kernel when the batch fills the chip (1 Mi envs in ONE launch, state = 665 MB) ----
+    # ---- supplementary: the single-step kernel when the batch fills the chip (1 Mi envs in ONE launch, state = 665 MB) ----
     scale = None
     if rank == 0 and not args.no_scale:
         Bs = 1 << 20
@@ -461,10 +546,10 @@ def run_ours(args):
         torch.cuda.synchronize()
         us = s0.elapsed_time(s1) / 8 * 1e3
         scale = {'envs_per_launch': Bs, 'us_per_launch': us, 'env_steps_per_s': Bs / us * 1e6, 'achieved_GBps': Bs * bytes_per_env / us / 1e3,
-                 'roofline_frac': Bs * bytes_per_env / us / 1e3 / peak, 'note': 'step kernel only, no resets; shows the issue-bound regime when the chip is full'}
+                 'roofline_frac': Bs * bytes_per_env / us / 1e3 / peak, 'note': 'single-step kernel only, no resets; shows the issue-bound regime when the chip is full'}
         del big, gb
 
-    # ---- e2e: the public host-facing API (HostStepper.step): pinned HOST buffers in and out every step. The robot is
+    # ---- e2e: the public host-facing API (HostStepper): pinned HOST buffers in and out every step. The robot is
     # driven from the host like the reference's Explorer loop does it: action up, obs/reward/done/info (+ the robot's
     # next ORCA decision) down, host waits for the results before the next step. ----
     import numpy as np
@@ -474,21 +559,21 @@ def run_ours(args):
     for env in envs[:P]:
         env.reset_seeds(rule=args.rule, use_queue=True)      # fresh scenes (the step-only pass ran past terminal states)
         env.set_robot_policy('external_xy')
-        steppers.append(HostStepper(env, next_orca_action=True))
+        steppers.append(HostStepper(env, next_orca_action=True, obs=args.e2e_obs))
     for st in steppers:
         st.step()
-        for _ in range(5):
+        for _ in range(40):                                  # into the episodes
             st.h_action.copy_(st.h_next_action); st.step()
-    ke = min(K, 400)
+    ke = 400
 
-    def e2e_rate(group):
+    def e2e_rate(group, n):
         """Round-robin over the batches in `group`; each visit = wait for the batch's previous step (results in host
         memory), host-side "policy" (apply the decision the device computed), enqueue its next step."""
         for st in group:
             st.launch()
         barrier()
         t0 = time.perf_counter()
-        for _ in range(ke):
+        for _ in range(n):
             for st in group:
                 st.wait()
                 np.copyto(st.np_action, st.np_next_action)
@@ -499,13 +584,13 @@ def run_ours(args):
         t = torch.tensor([dt_], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return world * B * ke * len(group) / float(t.item())
+        return world * B * n * len(group) / float(t.item())
 
-    e2e_single = e2e_rate(steppers[:1])                      # one batch, host blocks on every step (the reference's loop shape)
-    e2e_value = e2e_rate(steppers) if P > 1 else e2e_single  # P independent batches in flight
+    e2e_single = e2e_rate(steppers[:1], ke)                  # one batch, host blocks on every step (the reference's loop shape)
+    e2e_value = sorted(e2e_rate(steppers, ke) for _ in range(3))[1] if P > 1 else e2e_single  # P independent batches in flight, median of 3
     stepper = steppers[0]
     h2d, d2h = stepper.h2d_bytes, stepper.d2h_bytes
-    launches_note = 'timed region: %d step + %d scene-prefetch kernel launches (one CUDA graph, prefetch on side streams, every %d-th visit of a batch)' % (K, timed_prefetches, args.prefetch_every)
+    launches_note = 'timed region: %d rounds x (%d crowdsim_step_n launches of %d env-steps + %d scene-prefetch launches); per round every stream replays its graph of step launches and every side stream its graph of refills' % (rounds, pools, C, pools)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -531,20 +616,26 @@ def run_ours(args):
             parity = {'error': repr(ex)}
 
     if rank == 0:
-        line = {'metric': METRIC, 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': K, 'warmup': max(W, 3),
-                'ms_per_step': ms_max / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        line = {'metric': METRIC, 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+                'ms_per_step': ms_max / timed_steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'f64 state + f32 ORCA solver', 'data': 'synthetic',
                 'config': {'workload': WORKLOAD % (B, N, args.rule),
                            'envs_per_gpu': B, 'humans': N, 'l2': 'inputs larger than L2: %d rotating independent batches = %.0f MB of state' % (pools, pools * B * bytes_per_env / 1e6),
-                           'batches_in_flight': LANES,
+                           'batches_in_flight': S, 'steps_per_launch': C,
                            'parallelism': 'independent envs sharded over %d GPU(s), no data-path collective' % world},
-                'env_steps': {'performed': live_total, 'nominal': world * B * K,
+                'value_is': '%d independent %d-env batches in flight on %d streams (weak scaling unit = one GPU with its %d batches); the config-literal one-batch number is `single_batch`' % (S, B, S, pools),
+                'timed_region': {'replays': timed_steps // K, 'steps_per_replay': K, 'timed_steps': timed_steps, 'ms': ms_max,
+                                 'warmup_steps_done': warm_done,
+                                 'note': 'replays of K steps run back to back without a gap (streams joined only at the two ends of the region); ms_per_step = ms / timed_steps; '
+                                         'every batch was advanced >= %d steps before the region (steady mix of episode phases)' % (warm_done // pools)},
+                'rounds': round_stats,
+                'env_steps': {'performed': live_total, 'nominal': world * B * timed_steps,
                               'note': 'value = performed / time; performed is counted by the step kernel (episode step counters), nominal = envs x steps; they differ only if envs waited for a scene refill'},
                 'clocks': clocks, 'gpu_launches': int(launches), 'gpu_launches_note': launches_note,
                 'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                        'steps': ke, 'batches_in_flight': P, 'single_batch_blocking': e2e_single,
-                        'note': 'HostStepper.launch()/wait() round-robin over %d independent 4096-env batches: per batch-step a pinned host action buffer goes up and obs/reward/done/info/next ORCA action come down (byte counts are per batch-step), the host waits for a batch\'s results before it feeds that batch again; single_batch_blocking = one batch, host blocks on every step' % P},
-                'single_stream': single, 'parity_500_cases': parity, 'episodes': episodes, 'roofline': roofline, 'scale': scale, 'cpu_baseline': cpu}
+                        'steps': ke, 'batches_in_flight': P, 'single_batch_blocking': e2e_single, 'observation': args.e2e_obs,
+                        'note': 'HostStepper.launch()/wait() round-robin over %d independent %d-env batches: per batch-step a pinned host action buffer goes up and obs (%s)/reward/dmin/done/info/next ORCA action come down (byte counts are per batch-step), the host waits for a batch\'s results before it feeds that batch again; single_batch_blocking = one batch, host blocks on every step' % (P, B, 'float32 px,py,vx,vy per human' if args.e2e_obs == 'f32' else 'float64 state arrays')},
+                'single_batch': single, 'parity_500_cases': parity, 'episodes': episodes, 'roofline': roofline, 'scale': scale, 'cpu_baseline': cpu}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

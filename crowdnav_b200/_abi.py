@@ -37,7 +37,7 @@ class State(C.Structure):
 
 
 class StepIO(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ('action', 'action_out', 'reward', 'dmin', 'done', 'info')]
+    _fields_ = [(n, C.c_void_p) for n in ('action', 'action_out', 'reward', 'dmin', 'done', 'info', 'obs32')]
 
 
 class Episodes(C.Structure):

@@ -54,10 +54,13 @@ class Slab(object):
 
 
 def host_visible_layout(B, N):
-    """Step results first, the robot's next ORCA decision (produced by a later kernel) last."""
-    return [('h_pos', (B, N, 2), torch.float64), ('h_vel', (B, N, 2), torch.float64), ('reward', (B,), torch.float64),
-            ('dmin', (B,), torch.float64), ('action_out', (B, 2), torch.float64), ('done', (B,), torch.uint8),
-            ('info', (B,), torch.uint8), ('next_action', (B, 2), torch.float64)]
+    """Everything a host-side caller may read after a step, ordered so that both views are ONE contiguous range:
+    compact view  = [obs32 .. next_action]   float32 observation (crowdsim_step_io.obs32) + reward, dmin, done, info
+                    (+ the robot's next ORCA decision, produced by a later kernel): 114 B per env at N = 5
+    float64 view  = [reward .. h_vel]        the same scalars + the float64 state arrays themselves: 210 B per env"""
+    return [('obs32', (B, N, 4), torch.float32), ('reward', (B,), torch.float64), ('dmin', (B,), torch.float64),
+            ('done', (B,), torch.uint8), ('info', (B,), torch.uint8), ('next_action', (B, 2), torch.float64),
+            ('action_out', (B, 2), torch.float64), ('h_pos', (B, N, 2), torch.float64), ('h_vel', (B, N, 2), torch.float64)]
 
 
 class DeviceState(object):
@@ -203,6 +206,8 @@ class BatchedCrowdSim(object):
         self.action_out, self.next_action = self.out_slab['action_out'], self.out_slab['next_action']
         self.reward, self.dmin = self.out_slab['reward'], self.out_slab['dmin']
         self.done, self.info = self.out_slab['done'], self.out_slab['info']
+        self.obs32 = self.out_slab['obs32']
+        self.write_obs32 = False                 # step() also writes the float32 observation (HostStepper(obs='f32'))
         self._seed32 = torch.zeros(B, dtype=torch.int32, device=self.device)
 
     def set_robot_policy(self, kind):
@@ -302,7 +307,7 @@ class BatchedCrowdSim(object):
         prm = self.params()
         st = self.state.struct()
         io = _abi.StepIO(_ptr(self.action), _ptr(self.action_out), _ptr(self.reward), _ptr(self.dmin),
-                         _ptr(self.done), _ptr(self.info))
+                         _ptr(self.done), _ptr(self.info), _ptr(self.obs32) if self.write_obs32 else None)
         ep = self.episodes.struct() if self.episodes is not None else None
         ar = self.autoreset.struct() if self.autoreset is not None else None
         if n_steps == 1:
@@ -394,24 +399,34 @@ class HostStepper(object):
 
     One call = one CUDA graph replay: H2D copy of the robot actions from pinned memory, the fused step kernel, a refill of
     the consumed next-scene slots on a side branch (when env.enable_autoreset() was called), the robot's next ORCA
-    decision (optional, so a host loop can drive an ORCA robot), ONE D2H copy of the slab holding everything a caller
+    decision (optional, so a host loop can drive an ORCA robot), ONE D2H copy of the slab range holding what the caller
     reads, then a stream synchronise.
-    Buffers: self.h_action [B][2] (write before step()); results as views of the pinned host slab: self.h_pos, h_vel
-    [B][N][2], h_reward, h_dmin, h_done, h_info [B], h_action_out, h_next_action [B][2] (.numpy() views are free)."""
+    obs = 'f32' (default): the observation comes down as float32 (px, py, vx, vy) per human -- crowdsim_step_io.obs32, the
+    cast the reference's value-network policies apply anyway (multi_human_rl.py:43) -- 114 B per env and step at N = 5;
+    obs = 'f64': the float64 state arrays themselves, 210 B per env.
+    Buffers: self.h_action [B][2] (write before step()); results as views of the pinned host slab: self.h_obs32 [B][N][4]
+    (obs = 'f32') or self.h_pos, h_vel [B][N][2] (obs = 'f64'), h_reward, h_dmin, h_done, h_info [B], h_next_action [B][2]
+    (.numpy() views are free)."""
 
-    def __init__(self, env, next_orca_action=True):
-        self.env = env
+    def __init__(self, env, next_orca_action=True, obs='f32'):
+        assert obs in ('f32', 'f64')
+        self.env, self.obs = env, obs
         B, N, dev = env.B, env.human_num, env.device
         self.h_action = torch.zeros((B, 2), dtype=torch.float64).pin_memory()
         self.host_slab = Slab(host_visible_layout(B, N), 'cpu', pin=True)
         hs = self.host_slab
-        self.h_pos, self.h_vel, self.h_reward, self.h_dmin = hs['h_pos'], hs['h_vel'], hs['reward'], hs['dmin']
+        self.h_obs32, self.h_pos, self.h_vel, self.h_reward, self.h_dmin = hs['obs32'], hs['h_pos'], hs['h_vel'], hs['reward'], hs['dmin']
         self.h_done, self.h_info, self.h_action_out, self.h_next_action = hs['done'], hs['info'], hs['action_out'], hs['next_action']
         self.stream = torch.cuda.Stream(device=dev)
         self.side = torch.cuda.Stream(device=dev)
         self.done_event = torch.cuda.Event()
+        env.write_obs32 = (obs == 'f32')
+        if obs == 'f32':
+            lo, hi = 0, (hs.offsets['next_action'][0] + hs.offsets['next_action'][1]) if next_orca_action else (hs.offsets['info'][0] + hs.offsets['info'][1])
+        else:
+            lo, hi = hs.offsets['reward'][0], hs.nbytes
         self.h2d_bytes = self.h_action.numel() * 8
-        self.d2h_bytes = hs.nbytes
+        self.d2h_bytes = hi - lo
         self.kernels_per_step = 1 + (1 if env.autoreset is not None else 0) + (1 if next_orca_action else 0)
 
         def body():
@@ -425,10 +440,7 @@ class HostStepper(object):
             # was measured: 47 M vs 54 M env-steps/s -- the extra stream hand-offs cost more than the overlap gains.)
             if next_orca_action:
                 env.orca_act(env.next_action)
-                hs.buf.copy_(env.out_slab.buf, non_blocking=True)
-            else:
-                split = hs.offsets['next_action'][0]
-                hs.buf[:split].copy_(env.out_slab.buf[:split], non_blocking=True)
+            hs.buf[lo:hi].copy_(env.out_slab.buf[lo:hi], non_blocking=True)
             if env.autoreset is not None:
                 self.stream.wait_stream(self.side)     # join: the refill must be complete before the next step
         with torch.cuda.stream(self.stream):
@@ -442,7 +454,7 @@ class HostStepper(object):
         self.done_event.record(self.stream)            # creates the underlying cudaEvent_t
         self._event_h = self.done_event.cuda_event
         self._stream_h = self.stream.cuda_stream
-        self._result = ((self.h_pos, self.h_vel), self.h_reward, self.h_done, self.h_info)
+        self._result = ((self.h_obs32,) if obs == 'f32' else (self.h_pos, self.h_vel), self.h_reward, self.h_done, self.h_info)
         self.np_action, self.np_next_action = self.h_action.numpy(), self.h_next_action.numpy()
 
     def step(self):

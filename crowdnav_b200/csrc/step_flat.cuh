@@ -29,8 +29,8 @@
 // ladder, bookkeeping, install of the prefetched next scene when an episode ends), one store. That removes the launch gap
 // and the load/store stage from every step but the first. Results are bit-identical to n x crowdsim_step.
 //
-// Memory effects are written once at the end of the launch from the registers (both modes); rare events (an episode's
-// result row, parking, slot hand-over) are written when they happen.
+// The multi-step kernel writes its memory effects once, at the end of the launch, from the registers; rare events (an
+// episode's result row, parking, slot hand-over) are written when they happen. The single-step kernel stores as it goes.
 #pragma once
 #include "crowdsim_common.cuh"
 #include "orca_spec.cuh"
@@ -44,7 +44,9 @@ namespace cs {
 // attribute latency); the library only instantiates the full kernel (STAGE = 99).
 // Register budget of the single-step kernel: 6 resident blocks per SM (<= 80 registers) is neutral at 4096 envs and 9 %
 // faster at 65 k .. 1 M envs than the unconstrained build (round 1); the multi-step kernel serves launches that leave
-// the chip mostly empty and carries ~35 registers of state across steps: 3 blocks per SM (<= 168 registers).
+// the chip mostly empty and carries ~35 registers of state across steps: 4 blocks per SM (<= 128 registers, no spills).
+// Measured through bench.py (profiles/r02_multi_regs.txt): 3 / 4 / 5 blocks per SM = 131 / 128 / 96 registers give 790 / 848 /
+// 878 M env-steps/s with 16 batches in flight and 390 / 399 / 389 M for a single batch: 4 is the balance.
 // ROT: the robot is a unicycle (CROWDSIM_ROBOT_EXTERNAL_ROT, agent.py:115-135). A template parameter so that the double
 // precision cos / sin / fmod code (12 % of the round-1 kernel's SASS) is only present in the kernels that execute it.
 #ifndef CS_FLAT_WPB
@@ -54,7 +56,7 @@ namespace cs {
 #define CS_FLAT_MINBLOCKS 6
 #endif
 #ifndef CS_FLAT_MINBLOCKS_MULTI
-#define CS_FLAT_MINBLOCKS_MULTI 3
+#define CS_FLAT_MINBLOCKS_MULTI 4
 #endif
 
 template <int N, int STAGE = 99, bool ROT = false, bool MULTI = false, bool WARPQ = MULTI>
@@ -370,18 +372,18 @@ step_flat_kernel(const __grid_constant__ StepArgs A)
             }
             pos = make_double2(npx, npy); vel = make_double2(nvx, nvy);
             gtime = gtime + dt;
-            if constexpr (MULTI) { o_act = vel; o_reward = reward; o_dmin = dmin; o_done = done ? 1 : 0; o_info = info; any_live = true; }
-            else {                                           // single step: nothing to carry, the outputs leave at once
+            if constexpr (MULTI) { o_act = vel; o_reward = reward; o_dmin = dmin; o_done = done ? 1 : 0; o_info = info; any_live = true; dirty_kin = true; }
+            else {                                           // single step: nothing to carry, state and outputs leave at once
+                st2(A.st.r_pos, e, pos); st2(A.st.r_vel, e, vel); A.st.g_time[e] = gtime; if (ROT) A.st.r_theta[e] = theta;
                 if (A.io.action_out) st2(A.io.action_out, e, vel);
                 A.io.reward[e] = reward; A.io.dmin[e] = dmin; A.io.done[e] = done ? 1 : 0; A.io.info[e] = (uint8_t)info;
             }
-            dirty_kin = true;
             if (A.has_ep) {
                 const crowdsim_episodes &ep = A.ep;
                 const double disc = (ep_t < ep.discount_len) ? ep.discount[ep_t] : 0.0;
                 ep_ret = ep_ret + disc * reward; ep_t += 1;
-                if (info == CROWDSIM_INFO_DANGER) { ep_tc += 1; ep_mds += dmin; }
-                dirty_ep = true;
+                if (info == CROWDSIM_INFO_DANGER) { ep_tc += 1; ep_mds += dmin; if constexpr (!MULTI) { ep.ep_too_close[e] = ep_tc; ep.ep_min_dist_sum[e] = ep_mds; } }
+                if constexpr (MULTI) dirty_ep = true; else { ep.ep_return[e] = ep_ret; ep.ep_steps[e] = ep_t; }
                 if (done) {
                     if (ep_c >= 0) {
                         ep.res_info[ep_c] = (uint8_t)info; ep.res_steps[ep_c] = ep_t;
@@ -409,7 +411,16 @@ step_flat_kernel(const __grid_constant__ StepArgs A)
     }
     if (A.has_ar) {                                          // warp-uniform
         install = __shfl_sync(CS_FULL, install, rl) && env_ok;
-        if (install) {
+        if constexpr (!MULTI) {
+            // single step: the scene goes straight from the slot to the live state (ar_install_*: acquire on the slot flag, copy)
+            if (install) {
+                if (is_robot) ar_install_robot(A, e);
+                else {
+                    ar_install_human(A, e, N, a);
+                    if (A.io.obs32) { const double2 np_ = ld2_cg(A.ar.n_h_pos, hi); reinterpret_cast<float4 *>(A.io.obs32)[hi] = make_float4((float)np_.x, (float)np_.y, 0.f, 0.f); }
+                }
+            }
+        } else if (install) {
             // acquire on the slot flag (every lane that reads slot data), then the scene (agent.py:47-58 set(px,py,gx,gy,0,0,..))
             (void)ld_acquire_u8(A.ar.n_state + e);
             if (!is_robot) {
@@ -434,19 +445,26 @@ step_flat_kernel(const __grid_constant__ StepArgs A)
         // agent.py:122-135 holonomic step with the ORCA action (float32 values widened)
         const double hx = (double)nv.x, hy = (double)nv.y;
         pos = make_double2(pos.x + hx * dt, pos.y + hy * dt); vel = make_double2(hx, hy);
-        dirty_kin = true;
+        if constexpr (MULTI) dirty_kin = true;
+        else {
+            st2(A.st.h_pos, hi, pos); st2(A.st.h_vel, hi, vel);
+            if (A.io.obs32) reinterpret_cast<float4 *>(A.io.obs32)[hi] = make_float4((float)pos.x, (float)pos.y, nv.x, nv.y);
+        }
     }
     }   // step loop
 
-    // ---- one store of everything this launch changed ----
-    if (env_ok) {
+    // ---- multi-step launches: one store of everything the launch changed ----
+    if constexpr (MULTI) if (env_ok) {
         if (!is_robot) {
-            if (dirty_kin) { st2(A.st.h_pos, hi, pos); st2(A.st.h_vel, hi, vel); }
+            if (dirty_kin) {
+                st2(A.st.h_pos, hi, pos); st2(A.st.h_vel, hi, vel);
+                if (A.io.obs32) reinterpret_cast<float4 *>(A.io.obs32)[hi] = make_float4((float)pos.x, (float)pos.y, (float)vel.x, (float)vel.y);
+            }
             if (dirty_scene) { st2(A.st.h_goal, hi, goal); st2(A.st.h_attr, hi, attr); }
         } else {
             if (dirty_kin) { st2(A.st.r_pos, e, pos); st2(A.st.r_vel, e, vel); A.st.g_time[e] = gtime; if (ROT) A.st.r_theta[e] = theta; }
             if (dirty_scene) { st2(A.st.r_goal, e, goal); st2(A.st.r_attr, e, attr); }
-            if (MULTI && any_live) {                         // outputs of the env's last live step
+            if (any_live) {                                  // outputs of the env's last live step
                 if (A.io.action_out) st2(A.io.action_out, e, o_act);
                 A.io.reward[e] = o_reward; A.io.dmin[e] = o_dmin; A.io.done[e] = (uint8_t)o_done; A.io.info[e] = (uint8_t)o_info;
             }

@@ -198,7 +198,13 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepA
         if (is_robot) s.closest[le * L + N] = (double)install;     // the robot's own clearance slot is unused: env-wide flag
         __syncthreads();
         install = (s.closest[le * L + N] != 0.0) && env_ok;
-        if (install) { if (is_robot) ar_install_robot(A, e); else ar_install_human(A, e, N, a); }
+        if (install) {
+            if (is_robot) ar_install_robot(A, e);
+            else {
+                ar_install_human(A, e, N, a);
+                if (A.io.obs32) { const double2 np_ = ld2_cg(A.ar.n_h_pos, (size_t)e * N + a); reinterpret_cast<float4 *>(A.io.obs32)[(size_t)e * N + a] = make_float4((float)np_.x, (float)np_.y, 0.f, 0.f); }
+            }
+        }
         __syncthreads();
         if (install && is_robot) st_release_u8(A.ar.n_state + e, CROWDSIM_SLOT_EMPTY);
     }
@@ -206,8 +212,10 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepA
         // agent.py:122-135 holonomic step with the ORCA action (float32 values widened)
         const double hx = (double)nv.x, hy = (double)nv.y;
         const size_t i = (size_t)e * N + a;
-        st2(A.st.h_pos, i, make_double2(pos.x + hx * dt, pos.y + hy * dt));
+        const double2 np_ = make_double2(pos.x + hx * dt, pos.y + hy * dt);
+        st2(A.st.h_pos, i, np_);
         st2(A.st.h_vel, i, make_double2(hx, hy));
+        if (A.io.obs32) reinterpret_cast<float4 *>(A.io.obs32)[i] = make_float4((float)np_.x, (float)np_.y, nv.x, nv.y);
     }
 }
 

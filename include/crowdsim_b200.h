@@ -114,6 +114,10 @@ typedef struct crowdsim_step_io {
     double *dmin;         /* [B] min robot-human clearance this step (inf if N == 0) */
     uint8_t *done;        /* [B] */
     uint8_t *info;        /* [B] CROWDSIM_INFO_* */
+    float *obs32;         /* [B][N][4] or NULL: the observation after the step as float32 (px, py, vx, vy) per human -- the
+                             cast the value-network policies apply anyway (crowd_nav/policy/multi_human_rl.py:43); velocities
+                             are float32-valued ORCA outputs, so only the positions are rounded. For host-side callers: a
+                             third of the bytes of the float64 state arrays on the device->host link. */
 } crowdsim_step_io;
 
 /*

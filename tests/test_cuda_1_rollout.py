@@ -151,26 +151,32 @@ def test_update_memory_matches_single_env_explorer(cuda_env):
     assert (mem.states[:len(mem)].cpu() - ref_states).abs().max() < 2e-5
 
 
-def test_host_stepper_matches_oracle(cuda_env, oracle):
+@pytest.mark.parametrize('obs,N', [('f64', 5), ('f32', 5), ('f32', 8)])
+def test_host_stepper_matches_oracle(cuda_env, oracle, obs, N):
     """The host-facing step API (pinned buffers in/out, one CUDA graph per call): driving the robot from the host with the
-    'next action' the device computed reproduces the oracle's ORCA-robot episodes bit-exactly, array for array."""
+    'next action' the device computed reproduces the oracle's ORCA-robot episodes bit-exactly, array for array. obs='f32':
+    the compact observation (crowdsim_step_io.obs32, small-crowd and generic kernel) is the float32 cast of the oracle's
+    float64 state, exactly."""
     from crowdnav_b200.batched import HostStepper
     from crowdnav_b200 import _abi
-    B, N = 300, 5
+    B = 300
     host = oracle.HostState(B, N); io = oracle.HostStepIO(B)
     oracle.reset(host, np.arange(B) + 1000)
     env = cuda_env(B, N, robot_policy='external_xy')
     env.state.load_host(host)
-    stepper = HostStepper(env, next_orca_action=True)          # its warm-up + capture passes step the env: reload the scene
+    stepper = HostStepper(env, next_orca_action=True, obs=obs)   # its warm-up + capture passes step the env: reload the scene
     env.state.load_host(host)
     prm_ext = oracle.default_params(robot_policy=_abi.ROBOT_EXTERNAL_XY)
     act = oracle.orca_act(oracle.default_params(), host)
     for t in range(25):
         stepper.h_action.copy_(torch.from_numpy(act))
-        (h_pos, h_vel), rew, done, info = stepper.step()
+        ob, rew, done, info = stepper.step()
         io.action[...] = act
         oracle.step(prm_ext, host, io)
-        assert np.array_equal(h_pos.numpy(), host.h_pos) and np.array_equal(h_vel.numpy(), host.h_vel), t
+        if obs == 'f64':
+            assert np.array_equal(ob[0].numpy(), host.h_pos) and np.array_equal(ob[1].numpy(), host.h_vel), t
+        else:
+            assert np.array_equal(ob[0].numpy(), np.concatenate([host.h_pos, host.h_vel], axis=-1).astype(np.float32)), t
         assert np.array_equal(rew.numpy(), io.reward) and np.array_equal(done.numpy(), io.done) and np.array_equal(info.numpy(), io.info)
         act = oracle.orca_act(oracle.default_params(), host)
         assert np.array_equal(stepper.h_next_action.numpy(), act), t
@@ -187,7 +193,7 @@ def test_host_stepper_batches_in_flight(cuda_env, oracle):
     for q in range(P):
         host = oracle.HostState(B, N); oracle.reset(host, np.arange(B) + 5000 + 1000 * q)
         env = cuda_env(B, N, robot_policy='external_xy')
-        st = HostStepper(env, next_orca_action=True)
+        st = HostStepper(env, next_orca_action=True, obs='f64')
         env.state.load_host(host)
         hosts.append(host); ios.append(oracle.HostStepIO(B)); envs.append(env); steppers.append(st)
         acts.append(oracle.orca_act(oracle.default_params(), host))
