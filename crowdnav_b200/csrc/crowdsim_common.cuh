@@ -86,6 +86,17 @@ __host__ __device__ inline size_t stage_bytes(int epb, int L, int maxnb, int thr
     return b;
 }
 
+// Same staging + the crowd kernel's linearProgram3 queue (step_mid.cuh: mid_lp3_floats(), independent of the block size)
+// instead of the generic kernel's 2 x 4 x max_neighbors line / projected-line columns per thread.
+__host__ __device__ inline size_t stage_bytes_mid(int epb, int L, int lp3_floats)
+{
+    size_t agents = (size_t)epb * L;
+    size_t b = agents * (16 + 16 + 8 + 8 + 8 + 4 + 4 + 8) + (size_t)epb * 16;
+    b = (b + 15) & ~(size_t)15;
+    b += (size_t)lp3_floats * sizeof(float);
+    return b;
+}
+
 __device__ __forceinline__ Stage carve_stage(unsigned char *smem, int epb, int L, int maxnb, int threads)
 {
     Stage s; const size_t agents = (size_t)epb * L;

@@ -167,6 +167,24 @@ ORCA_HD __forceinline__ V2 lp2_init(V2 opt, float radius)
     return opt;
 }
 
+// Sorted-list form of RVO2's insertAgentNeighbor for the crowd kernel (step_mid.cuh): (td, tj) = the <= M nearest
+// candidates seen so far, ascending; a candidate is inserted with an unrolled compare-and-shift network (static register
+// indexing). Strict <: a candidate goes BEHIND equal distances (ties keep scan order) and one that is not nearer than the
+// M-th entry is dropped (RVO2: rangeSq = list.back() once the list is full). Absent entries hold +inf; pass dd = +inf for
+// a candidate that is out of range / not a candidate (never inserted).
+template <int M>
+ORCA_HD __forceinline__ void insert_sorted(float dd, int j, float (&td)[M], int (&tj)[M])
+{
+    #pragma unroll
+    for (int kk = M - 1; kk >= 0; --kk) {                     // downwards: entry kk - 1 still holds its old value
+        const int km = kk > 0 ? kk - 1 : 0;
+        const bool lt = dd < td[kk];
+        const bool ltp = (kk > 0) && (dd < td[km]);
+        td[kk] = ltp ? td[km] : (lt ? dd : td[kk]);
+        tj[kk] = ltp ? tj[km] : (lt ? j : tj[kk]);
+    }
+}
+
 // ---- linearProgram3 spread over lanes (step_flat.cuh, step_mid.cuh) ----------------------------------------------------
 // RVO2's linearProgram3 visits the lines i = begin .. n-1; for a line that is violated by more than the running `distance`
 // it builds the lines j < i projected onto i and solves linearProgram2 over them in direction-optimisation mode, STARTING

@@ -70,15 +70,28 @@ __device__ __forceinline__ void ar_install_robot(const StepArgs &A, int e)
 
 }  // namespace cs
 #include "step_flat.cuh"
+#include "step_mid.cuh"
 namespace cs {
 
-__global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepArgs A)
+// Resident blocks per SM the crowd kernel is compiled for. BASELINE config 4 (4096 envs x 21 agents = 683 blocks of 126
+// threads) needs 5 per SM to be resident in ONE wave on 148 SMs; at 4 (119 registers) the launch ran 1.15 waves.
+#ifndef CS_MID_MINBLOCKS
+#define CS_MID_MINBLOCKS 5
+#endif
+
+// MID = false: the generic kernel of round 1 (RVO2's sequential code on per-thread shared-memory columns; any
+// max_neighbors <= 10; kept as the A/B partner of the two fast kernels in the tests: crowdsim_debug_force_generic).
+// MID = true: the crowd kernel for N > 5 (step_mid.cuh: register-resident lines, speculative LPs, compacted lp3).
+template <bool MID>
+__global__ void __launch_bounds__(MID ? 128 : 256, MID ? CS_MID_MINBLOCKS : 1) step_kernel(const __grid_constant__ StepArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int s_qcount;
     const int T = blockDim.x, tid = threadIdx.x;
     const int N = A.N, L = A.L;
     const KParams &k = A.k;
     const Stage s = carve_stage(smem, A.EPB, L, k.nb_alloc, T);
+    if (MID && tid == 0) s_qcount = 0;
 
     const int le = tid / L, a = tid - le * L;
     const int e = blockIdx.x * A.EPB + le;
@@ -105,7 +118,8 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepA
     // ---- ORCA solves: every human lane; the robot lane iff the robot runs ORCA ----
     orca::V2 nv = orca::mk(0.f, 0.f);
     const bool solve = live && (!is_robot || k.robot_policy == CROWDSIM_ROBOT_ORCA) && !(A.act_only && !is_robot);
-    if (solve) nv = orca_predict(s, k, le, a, N, L, pos, goal, attr.y, tid, T);
+    if constexpr (MID) nv = mid_solve<kMidM>(s, k, solve, le, a, N, L, pos, goal, attr.y, tid, T, s.lines, &s_qcount);
+    else if (solve) nv = orca_predict(s, k, le, a, N, L, pos, goal, attr.y, tid, T);
 
     if (A.act_only) {
         if (live && is_robot) st2(A.io.action_out, e, make_double2((double)nv.x, (double)nv.y));
@@ -293,13 +307,16 @@ static int launch(const crowdsim_params *prm, int B, int N, const crowdsim_state
     }
     const int threads = A.EPB * A.L;
     const int blocks = (B + A.EPB - 1) / A.EPB;
-    const size_t smem = stage_bytes(A.EPB, A.L, A.k.nb_alloc, threads);
+    const bool mid = !g_force_generic && N > 5;              // (N = 0 and the forced A/B route stay on the generic kernel)
+    const size_t smem = mid ? stage_bytes_mid(A.EPB, A.L, mid_lp3_floats()) : stage_bytes(A.EPB, A.L, A.k.nb_alloc, threads);
     if (smem > 48 * 1024) {                                  // (a per-device attribute; setting it again is cheap)
-        cudaError_t err = cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t err = mid ? cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                              : cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return (int)err;
     }
     for (int rep = 0; rep < n_steps; ++rep) {
-        step_kernel<<<blocks, threads, smem, stream>>>(A);
+        if (mid) step_kernel<true><<<blocks, threads, smem, stream>>>(A);
+        else step_kernel<false><<<blocks, threads, smem, stream>>>(A);
         ++g_launches;
     }
     return (int)cudaGetLastError();

@@ -7,6 +7,7 @@
 //   D  lp3 as independent per-line sub-problems + lp3_outer_scan (the lane-parallel pass)      vs  orc_lp3
 //   F  lp3 on lanes: (i, j) pair projections + speculative per-line sub-problems (lp3_project_pair, lp3_sub_spec<4> and <9>)
 //      + lp3_outer_scan                                                                        vs  orc_lp3
+//   H  insert_sorted<10> (sorted register list of the crowd kernel, 20-60 candidates incl. ties) vs  orc_insert_neighbor
 //   E  neighbour_order (pair-wise ranks + packed indices of the small-crowd kernel)            vs  orc_insert_neighbor
 // Build (tests/test_native_cpu.py): nvcc -O2 --fmad=false -Xcompiler -ffp-contract=off -std=c++17 lp_fuzz.cu
 // Usage: lp_fuzz <cases> <seed>; prints coverage counters; exit code 0 iff every comparison was bit-identical.
@@ -112,6 +113,30 @@ static bool check_order(long *cov)
     return true;
 }
 
+// ---- H: the crowd kernel's neighbour list: n candidates (some out of range, many exact ties), capacity 10 and smaller ----
+static bool check_sorted_insert(long *cov)
+{
+    constexpr int M = 10;
+    const int n = 1 + rnd() % 63, max_nb = (rnd() % 4 == 0) ? 1 + (int)(rnd() % 10) : 10;
+    const float range_sq = 100.0f, inf = __builtin_inff();
+    const bool ties = rnd() % 3 == 0;
+    float td[M]; int tj[M]; for (int k = 0; k < M; ++k) { td[k] = inf; tj[k] = 0; }
+    float nd[M]; int ni[M]; int cnt = 0; float rs = range_sq; int in_range = 0;
+    for (int j = 0; j < n; ++j) {
+        const float x = ties ? (float)(rnd() % 5) * 0.5f : uni(-11.f, 11.f), y = ties ? (float)(rnd() % 4) : uni(-11.f, 11.f);
+        const float d = x * x + y * y;
+        const bool in = (rnd() % 10 != 0) && d < range_sq;
+        orca::insert_sorted<M>(in ? d : inf, j, td, tj);
+        in_range += in;
+        if (in) orc_insert_neighbor(d, j, nd, ni, &cnt, max_nb, &rs);
+    }
+    int nl = in_range < max_nb ? in_range : max_nb;
+    if (nl != cnt) { printf("H count mismatch %d vs %d\n", nl, cnt); return false; }
+    for (int k = 0; k < nl; ++k) if (tj[k] != ni[k] || !same(td[k], nd[k])) { printf("H order mismatch at %d (n=%d max_nb=%d)\n", k, n, max_nb); return false; }
+    cov[7] += 1;
+    return true;
+}
+
 int main(int argc, char **argv)
 {
     const long cases = argc > 1 ? atol(argv[1]) : 200000;
@@ -153,8 +178,10 @@ int main(int argc, char **argv)
             }
         }
         if (!check_case<5>(n, ol, radius, opt, cov)) { printf("case %ld kind %d\n", c, kind); return 1; }
+        if (n > 5) { long dummy[8] = {0}; if (!check_case<10>(n, ol, radius, opt, dummy)) { printf("case %ld kind %d (M = 10)\n", c, kind); return 1; } cov[1] += dummy[1]; }
+        if (!check_sorted_insert(cov)) { printf("case %ld\n", c); return 1; }
         if (!(check_order<5>(cov) && check_order<4>(cov) && check_order<2>(cov) && check_order<1>(cov))) { printf("case %ld\n", c); return 1; }
     }
-    printf("ok cases=%ld lp3_needed=%ld speculative_checked=%ld overlapping_pairs=%ld forced_parallel_lines=%ld neighbour_orders=%ld neighbour_ties=%ld lane_lp3_checked=%ld\n", cases, cov[0], cov[1], cov[2], cov[3], cov[4], cov[5], cov[6]);
+    printf("ok cases=%ld lp3_needed=%ld speculative_checked=%ld overlapping_pairs=%ld forced_parallel_lines=%ld neighbour_orders=%ld neighbour_ties=%ld lane_lp3_checked=%ld sorted_lists=%ld\n", cases, cov[0], cov[1], cov[2], cov[3], cov[4], cov[5], cov[6], cov[7]);
     return 0;
 }

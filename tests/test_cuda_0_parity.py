@@ -81,10 +81,12 @@ def _default_kernel_routing():
     (2, 1, 'external_xy', 0), (2, 0, 'orca', 0), (1, 0, 'orca', 0), (1, 1, 'orca', 0), (5, 0, 'external_rot', 0),
     (5, 0, 'orca', 1), (5, 1, 'orca', 1), (1, 0, 'orca', 1), (2, 1, 'external_xy', 1), (5, 0, 'external_rot', 1),
     (10, 1, 'orca', 0), (11, 0, 'orca', 0), (20, 0, 'orca', 0), (20, 1, 'external_xy', 0), (33, 1, 'orca', 0), (63, 1, 'orca', 0),
-    (0, 0, 'orca', 0), (6, 1, 'orca', 0)])
+    (0, 0, 'orca', 0), (6, 1, 'orca', 0), (7, 0, 'orca', 0), (9, 1, 'external_xy', 0), (20, 1, 'orca', 0),
+    (20, 0, 'orca', 1), (11, 1, 'orca', 1), (6, 0, 'external_xy', 1)])
 def test_step_random_scenes_bit_exact(cuda_env, oracle, N, vis, policy, generic):
     """Dense random scenes (many overlapping agents -> collision branch, lp3 fallback, 10-of-N truncation),
-    8 consecutive steps, every state/output array compared for equality with the CPU oracle."""
+    8 consecutive steps, every state/output array compared for equality with the CPU oracle. Routing: N <= 5 small-crowd
+    kernel, N > 5 crowd kernel (step_mid.cuh); generic = 1 forces the round-1 generic kernel (A/B partner of both)."""
     B = 1500 if N <= 20 else 300
     host = _random_host_state(oracle, B, N, seed=100 + N)
     env = cuda_env(B, N, robot_visible=bool(vis), robot_policy=policy)

@@ -29,5 +29,6 @@ def test_host_compiled_solver_matches_oracle_bitwise(fuzz_binary, seed):
     # the interesting branches are really exercised
     assert int(fields['lp3_needed']) > 100000 and int(fields['speculative_checked']) > 500000
     assert int(fields['overlapping_pairs']) > 100000 and int(fields['forced_parallel_lines']) > 100000
+    assert int(fields['sorted_lists']) == 1000000                                                    # part H
     assert int(fields['lane_lp3_checked']) == int(fields['lp3_needed'])                              # part F
     assert int(fields['neighbour_orders']) == 4000000 and int(fields['neighbour_ties']) > 1000000    # part E, M = 5, 4, 2, 1
