@@ -55,7 +55,7 @@ class ResetArgs(C.Structure):
                 ('human_v_pref', C.c_double), ('robot_radius', C.c_double), ('robot_v_pref', C.c_double),
                 ('discomfort_dist', C.c_double), ('randomize_attributes', C.c_int32),
                 ('case_counter', C.c_void_p), ('case_total', C.c_int32),
-                ('seed_base', C.c_uint32)]
+                ('seed_base', C.c_uint32), ('case_first', C.c_int32), ('case_wrap', C.c_int32)]
 
 
 class AutoReset(C.Structure):
@@ -93,7 +93,7 @@ def declare(lib, prefix='crowdsim_', with_stream=True):
 EXPORTS = ('crowdsim_abi_version', 'crowdsim_device_check', 'crowdsim_launch_count', 'crowdsim_debug_force_generic', 'crowdsim_graph_launch',
            'crowdsim_event_wait', 'crowdsim_step', 'crowdsim_step_n',
            'crowdsim_orca_act', 'crowdsim_reset', 'crowdsim_prefetch_scenes', 'crowdsim_pack_joint', 'crowdsim_lookahead_pack',
-           'crowdsim_lookahead_humans', 'crowdsim_occupancy_maps')
+           'crowdsim_lookahead_humans', 'crowdsim_occupancy_maps', 'crowdsim_human_times', 'crowdsim_onestep_lookahead')
 
 # CROWDSIM_B200_LIB selects another build of the SAME library (A/B runs of kernel variants, scripts/gpu_variants.sh);
 # it is never a fallback: the named file must exist.
@@ -129,6 +129,10 @@ def load():
         lib.crowdsim_lookahead_humans.restype = C.c_int
         lib.crowdsim_occupancy_maps.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
         lib.crowdsim_occupancy_maps.restype = C.c_int
+        lib.crowdsim_human_times.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.POINTER(State), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        lib.crowdsim_human_times.restype = C.c_int
+        lib.crowdsim_onestep_lookahead.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.POINTER(State), C.POINTER(StepIO), C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.crowdsim_onestep_lookahead.restype = C.c_int
         declare(lib)
         if lib.crowdsim_abi_version() != ABI_VERSION:
             raise CudaLibraryMissing('ABI version mismatch: library %d, python %d'

@@ -24,9 +24,17 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+def max_episode_steps(time_limit, time_step):
+    """Steps an episode can last: the timeout fires on the first step with global_time >= time_limit - 1
+    (crowd_sim.py:368; 97 with the default 25 s / 0.25 s). +2 of slack."""
+    import math
+    return int(math.ceil(float(time_limit) / float(time_step))) + 2
+
+
 def discount_table(gamma, time_step, v_pref, n=128):
     """explorer.py:71-72: pow(gamma, t * time_step * v_pref) for t = 0..n-1, computed with C pow on the host so the
-    device-side discounted return is bit-identical to the reference's."""
+    device-side discounted return is bit-identical to the reference's. n must cover the longest episode
+    (max_episode_steps): the kernels treat steps beyond the table as undiscounted-to-zero."""
     return [pow(gamma, t * time_step * v_pref) for t in range(n)]
 
 
@@ -98,13 +106,13 @@ class DeviceState(object):
 class EpisodeBuffers(object):
     """crowdsim_episodes: slot accumulators + per-case results of Explorer.run_k_episodes (explorer.py:35-72)."""
 
-    def __init__(self, B, k, device, gamma, time_step, v_pref):
+    def __init__(self, B, k, device, gamma, time_step, v_pref, max_steps=128):
         i32 = lambda n, v=0: torch.full((n,), v, dtype=torch.int32, device=device)  # noqa: E731
         f64 = lambda *s: torch.zeros(s, dtype=torch.float64, device=device)  # noqa: E731
         self.k = k
         self.ep_case, self.ep_steps, self.ep_too_close = i32(B, -1), i32(B), i32(B)
         self.ep_return, self.ep_min_dist_sum = f64(B), f64(B)
-        self.discount = torch.tensor(discount_table(gamma, time_step, v_pref), dtype=torch.float64, device=device)
+        self.discount = torch.tensor(discount_table(gamma, time_step, v_pref, max(128, max_steps)), dtype=torch.float64, device=device)
         self.res_info = torch.zeros(k, dtype=torch.uint8, device=device)
         self.res_steps, self.res_too_close = i32(k), i32(k)
         self.res_time, self.res_return, self.res_min_dist_sum = f64(k), f64(k), f64(k)
@@ -164,7 +172,7 @@ class BatchedCrowdSim(object):
         # ORCA constants (orca.py:61-64)
         self.neighbor_dist = 10.0; self.max_neighbors = 10; self.time_horizon = 5.0
         self.state = None; self.episodes = None; self.autoreset = None
-        self._case_counter = None; self._case_total = 0; self._seed_base = 0
+        self._case_counter = None; self._case_total = 0; self._seed_base = 0; self._case_first = 0; self._case_wrap = 0
         self._ar_rule = None; self._ar_seed_stride = 0
 
     # ---- configuration -------------------------------------------------------------------------------------------
@@ -225,7 +233,8 @@ class BatchedCrowdSim(object):
 
     # ---- episodes ------------------------------------------------------------------------------------------------
     def track_episodes(self, k, gamma=0.9):
-        self.episodes = EpisodeBuffers(self.B, k, self.device, gamma, self.time_step, self.robot_v_pref)
+        self.episodes = EpisodeBuffers(self.B, k, self.device, gamma, self.time_step, self.robot_v_pref,
+                                       max_steps=max_episode_steps(self.time_limit, self.time_step))
         return self.episodes
 
     # ---- reset ---------------------------------------------------------------------------------------------------
@@ -253,7 +262,8 @@ class BatchedCrowdSim(object):
         return _abi.ResetArgs(_ptr(mask), _ptr(self._seed32), int(seed_stride) % 2 ** 32, _abi.RULES[rule], self.circle_radius,
                               self.square_width, self.human_radius, self.human_v_pref, self.robot_radius, self.robot_v_pref,
                               self.discomfort_dist, int(bool(self.randomize_attributes)),
-                              _ptr(self._case_counter) if q else None, self._case_total if q else 0, self._seed_base if q else 0)
+                              _ptr(self._case_counter) if q else None, self._case_total if q else 0, self._seed_base if q else 0,
+                              self._case_first if q else 0, self._case_wrap if q else 0)
 
     def reset_seeds(self, seeds=None, mask=None, rule='circle_crossing', seed_stride=0, use_queue=False):
         """crowdsim_reset for the envs selected by `mask` (uint8 device tensor, None = all) from the per-slot seeds.
@@ -266,8 +276,9 @@ class BatchedCrowdSim(object):
         a = self._reset_args(mask, rule, seed_stride, use_queue)
         st = self.state.struct()
         ep = self.episodes.struct() if self.episodes is not None else None
-        rc = self.lib.crowdsim_reset(C.byref(a), self.B, self.human_num, C.byref(st),
-                                     C.byref(ep) if ep is not None else None, self._stream())
+        with torch.cuda.device(self.device):
+            rc = self.lib.crowdsim_reset(C.byref(a), self.B, self.human_num, C.byref(st),
+                                         C.byref(ep) if ep is not None else None, self._stream())
         _abi.check(rc, 'crowdsim_reset')
         self._keep = (mask, a)
 
@@ -277,7 +288,12 @@ class BatchedCrowdSim(object):
         env slots pull the next case on device when their episode ends (Explorer.run_k_episodes with k > slots)."""
         self._case_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._case_total = int(total)
-        self._seed_base = (_PHASE_OFFSET[phase] + int(first_case)) % 2 ** 32
+        size = self.case_size[phase] if self.case_size else 0
+        if 0 < size < 2 ** 31:
+            # the run may cross the end of the phase's case range: case numbers wrap like crowd_sim.py:283 does
+            self._seed_base, self._case_first, self._case_wrap = _PHASE_OFFSET[phase], int(first_case) % size, size
+        else:                                                # train: 2**32 - 2001 cases, no wrap within int32 counters
+            self._seed_base, self._case_first, self._case_wrap = (_PHASE_OFFSET[phase] + int(first_case)) % 2 ** 32, 0, 0
 
     def enable_autoreset(self, rule='circle_crossing', seed_stride=0):
         """Allocate the per-slot next-scene buffers; step() then re-initialises finished envs in the same launch.
@@ -290,7 +306,8 @@ class BatchedCrowdSim(object):
     def prefetch(self):
         a = self._reset_args(None, self._ar_rule, self._ar_seed_stride, True)
         ar = self.autoreset.struct()
-        rc = self.lib.crowdsim_prefetch_scenes(C.byref(a), self.B, self.human_num, C.byref(ar), self._stream())
+        with torch.cuda.device(self.device):
+            rc = self.lib.crowdsim_prefetch_scenes(C.byref(a), self.B, self.human_num, C.byref(ar), self._stream())
         _abi.check(rc, 'crowdsim_prefetch_scenes')
 
     # ---- step ----------------------------------------------------------------------------------------------------
@@ -311,13 +328,15 @@ class BatchedCrowdSim(object):
         ep = self.episodes.struct() if self.episodes is not None else None
         ar = self.autoreset.struct() if self.autoreset is not None else None
         if n_steps == 1:
-            rc = self.lib.crowdsim_step(C.byref(prm), self.B, self.human_num, C.byref(st), C.byref(io),
-                                        C.byref(ep) if ep is not None else None, C.byref(ar) if ar is not None else None,
-                                        self._stream())
+            with torch.cuda.device(self.device):
+                rc = self.lib.crowdsim_step(C.byref(prm), self.B, self.human_num, C.byref(st), C.byref(io),
+                                            C.byref(ep) if ep is not None else None, C.byref(ar) if ar is not None else None,
+                                            self._stream())
         else:
-            rc = self.lib.crowdsim_step_n(C.byref(prm), self.B, self.human_num, C.byref(st), C.byref(io),
-                                          C.byref(ep) if ep is not None else None, C.byref(ar) if ar is not None else None,
-                                          int(n_steps), self._stream())
+            with torch.cuda.device(self.device):
+                rc = self.lib.crowdsim_step_n(C.byref(prm), self.B, self.human_num, C.byref(st), C.byref(io),
+                                              C.byref(ep) if ep is not None else None, C.byref(ar) if ar is not None else None,
+                                              int(n_steps), self._stream())
         _abi.check(rc, 'crowdsim_step')
         return self.observation(), self.reward, self.done, self.info
 
@@ -328,7 +347,8 @@ class BatchedCrowdSim(object):
     def orca_act(self, out=None):
         out = self.action_out if out is None else out
         prm = self.params(); st = self.state.struct()
-        rc = self.lib.crowdsim_orca_act(C.byref(prm), self.B, self.human_num, C.byref(st), _ptr(out), self._stream())
+        with torch.cuda.device(self.device):
+            rc = self.lib.crowdsim_orca_act(C.byref(prm), self.B, self.human_num, C.byref(st), _ptr(out), self._stream())
         _abi.check(rc, 'crowdsim_orca_act')
         return out
 
@@ -342,7 +362,8 @@ class BatchedCrowdSim(object):
         if out is None:
             out = torch.empty((self.B, self.human_num, 13), dtype=torch.float32, device=self.device)
         st = self.state.struct()
-        rc = self.lib.crowdsim_pack_joint(self.B, self.human_num, C.byref(st), int(unicycle), _ptr(out), self._stream())
+        with torch.cuda.device(self.device):
+            rc = self.lib.crowdsim_pack_joint(self.B, self.human_num, C.byref(st), int(unicycle), _ptr(out), self._stream())
         _abi.check(rc, 'crowdsim_pack_joint')
         return out
 
@@ -354,8 +375,9 @@ class BatchedCrowdSim(object):
         if out_reward is None:
             out_reward = torch.empty((self.B, A), dtype=torch.float64, device=self.device)
         prm = self.params(); st = self.state.struct()
-        rc = self.lib.crowdsim_lookahead_pack(C.byref(prm), self.B, self.human_num, C.byref(st), _ptr(actions), A,
-                                              int(unicycle), _ptr(out_states), _ptr(out_reward), self._stream())
+        with torch.cuda.device(self.device):
+            rc = self.lib.crowdsim_lookahead_pack(C.byref(prm), self.B, self.human_num, C.byref(st), _ptr(actions), A,
+                                                  int(unicycle), _ptr(out_states), _ptr(out_reward), self._stream())
         _abi.check(rc, 'crowdsim_lookahead_pack')
         return out_states, out_reward
 
@@ -373,10 +395,39 @@ class BatchedCrowdSim(object):
         if out_vel is None:
             out_vel = torch.empty((self.B, self.human_num, 2), dtype=torch.float64, device=self.device)
         prm = self.params(); st = self.state.struct()
-        rc = self.lib.crowdsim_lookahead_humans(C.byref(prm), self.B, self.human_num, C.byref(st), _ptr(out_pos), _ptr(out_vel),
-                                                self._stream())
+        with torch.cuda.device(self.device):
+            rc = self.lib.crowdsim_lookahead_humans(C.byref(prm), self.B, self.human_num, C.byref(st), _ptr(out_pos), _ptr(out_vel),
+                                                    self._stream())
         _abi.check(rc, 'crowdsim_lookahead_humans')
         return out_pos, out_vel
+
+    def onestep_lookahead(self, actions, out_pos=None, out_vel=None):
+        """env.onestep_lookahead for one action per env ([B][2] float64 device tensor): ((next_h_pos, next_h_vel, radius),
+        reward, done, info) like step(), nothing mutated (crowdsim_onestep_lookahead)."""
+        B, N = self.B, self.human_num
+        out_pos = torch.empty((B, N, 2), dtype=torch.float64, device=self.device) if out_pos is None else out_pos
+        out_vel = torch.empty((B, N, 2), dtype=torch.float64, device=self.device) if out_vel is None else out_vel
+        if actions.data_ptr() != self.action.data_ptr():
+            self.action.copy_(actions, non_blocking=True)
+        prm = self.params(); st = self.state.struct()
+        io = _abi.StepIO(_ptr(self.action), _ptr(self.action_out), _ptr(self.reward), _ptr(self.dmin), _ptr(self.done), _ptr(self.info), None)
+        with torch.cuda.device(self.device):
+            rc = self.lib.crowdsim_onestep_lookahead(C.byref(prm), B, N, C.byref(st), C.byref(io), _ptr(out_pos), _ptr(out_vel), self._stream())
+        _abi.check(rc, 'crowdsim_onestep_lookahead')
+        return (out_pos, out_vel, self.state.h_attr[..., 0]), self.reward, self.done, self.info
+
+    def human_times(self, human_times=None, max_steps=4000):
+        """CrowdSim.get_human_times for every env (crowdsim_human_times): (human_times [B][N], global_time [B], final
+        positions [B][N+1][2] robot first). `human_times`: arrivals recorded during the episode (0 = not yet)."""
+        B, N = self.B, self.human_num
+        ht = torch.zeros((B, N), dtype=torch.float64, device=self.device) if human_times is None else human_times.to(self.device, torch.float64).contiguous()
+        gt = torch.empty((B,), dtype=torch.float64, device=self.device)
+        fp = torch.empty((B, N + 1, 2), dtype=torch.float64, device=self.device)
+        prm = self.params(); st = self.state.struct()
+        with torch.cuda.device(self.device):
+            rc = self.lib.crowdsim_human_times(C.byref(prm), B, N, C.byref(st), _ptr(ht), _ptr(gt), _ptr(fp), int(max_steps), self._stream())
+        _abi.check(rc, 'crowdsim_human_times')
+        return ht, gt, fp
 
     def occupancy_maps(self, h_pos=None, h_vel=None, cell_num=4, cell_size=1.0, om_channel_size=3, out=None):
         """MultiHumanRL.build_occupancy_maps (multi_human_rl.py:109-163) for every env: [B][N][cell_num^2 * channels]
@@ -387,8 +438,9 @@ class BatchedCrowdSim(object):
         h_vel = self.state.h_vel if h_vel is None else h_vel
         if out is None:
             out = torch.empty((self.B, self.human_num, cell_num * cell_num * om_channel_size), dtype=torch.float32, device=self.device)
-        rc = self.lib.crowdsim_occupancy_maps(self.B, self.human_num, _ptr(h_pos), _ptr(h_vel), int(cell_num), float(cell_size),
-                                              int(om_channel_size), _ptr(out), self._stream())
+        with torch.cuda.device(self.device):
+            rc = self.lib.crowdsim_occupancy_maps(self.B, self.human_num, _ptr(h_pos), _ptr(h_vel), int(cell_num), float(cell_size),
+                                                  int(om_channel_size), _ptr(out), self._stream())
         _abi.check(rc, 'crowdsim_occupancy_maps')
         return out
 

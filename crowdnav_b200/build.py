@@ -15,11 +15,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 TARGET = os.path.join(CSRC, 'libcrowdsim_b200.so')
-SOURCES = ['step_kernel.cu', 'reset_kernel.cu', 'pack_kernel.cu']
-HEADERS = ['crowdsim_common.cuh', 'orca_device.cuh', 'step_flat.cuh', 'orca_spec.cuh', os.path.join('..', '..', 'include', 'crowdsim_b200.h')]
+SOURCES = ['step_kernel.cu', 'reset_kernel.cu', 'pack_kernel.cu', 'times_kernel.cu']
+HEADERS = ['crowdsim_common.cuh', 'orca_device.cuh', 'step_flat.cuh', 'step_mid.cuh', 'orca_spec.cuh', os.path.join('..', '..', 'include', 'crowdsim_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '--fmad=false',
               '-prec-div=true', '-prec-sqrt=true', '-ftz=false', '-std=c++17',
-              '-Xcompiler', '-fPIC', '-shared', '-cudart', 'shared']
+              '-Xcompiler', '-fPIC', '-shared', '-cudart', 'shared', '--threads', '4']
 
 
 def _nvcc():

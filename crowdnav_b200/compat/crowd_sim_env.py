@@ -7,7 +7,7 @@
 One env.step = one crowdsim_step launch on a one-env batch + a device->host read of the few scalars the caller sees.
 The humans' ORCA solves, the collision / reward / terminal logic and the integration all run in the CUDA kernels; the
 Human / Robot objects are host mirrors refreshed after every call. No CPU fallback: without the CUDA library this
-raises. render() and get_human_times() are out of scope.
+raises. render() is out of scope.
 """
 import logging
 
@@ -34,6 +34,7 @@ class CrowdSim(object):
         self.square_width = None; self.circle_radius = None; self.human_num = None
         self.states = None; self.action_values = None; self.attention_weights = None
         self._engine = None; self._config_human_num = None
+        self._act_host = torch.zeros((1, 2), dtype=torch.float64)
 
     # ---- crowd_sim.py:51-79 ----
     def configure(self, config):
@@ -142,39 +143,47 @@ class CrowdSim(object):
     # ---- crowd_sim.py:317-420 ----
     def step(self, action, update=True):
         eng = self._engine
-        if isinstance(action, ActionRot):
-            act = torch.tensor([[action.v, action.r]], dtype=torch.float64)
-        else:
-            act = torch.tensor([[action.vx, action.vy]], dtype=torch.float64)
-        s = eng.state
-        snap = None
-        if not update:                                         # nothing may be mutated (crowd_sim.py:414-416)
-            snap = [getattr(s, f).clone() for f in s.FIELDS] + [s.active.clone()]
-        else:
-            self.states.append([self.robot.get_full_state(), [h.get_full_state() for h in self.humans]])
-            if hasattr(self.robot.policy, 'action_values'):
-                self.action_values.append(self.robot.policy.action_values)
-            if hasattr(self.robot.policy, 'get_attention_weights'):
-                self.attention_weights.append(self.robot.policy.get_attention_weights())
-        eng.step(act.to(eng.device))
+        self._act_host[0, 0], self._act_host[0, 1] = (action.v, action.r) if isinstance(action, ActionRot) else (action.vx, action.vy)
+        act = self._act_host.to(eng.device, non_blocking=True)
+        if not update:
+            # crowd_sim.py:414-416: nothing is mutated -- one non-mutating kernel (crowdsim_onestep_lookahead), one read-back
+            (npos, nvel, _), _, _, _ = eng.onestep_lookahead(act)
+            hp, hv = npos[0].tolist(), nvel[0].tolist()
+            reward, dmin, done, code = float(eng.reward[0]), float(eng.dmin[0]), bool(eng.done[0]), int(eng.info[0])
+            ob = [ObservableState(hp[i][0], hp[i][1], hv[i][0], hv[i][1], h.radius) for i, h in enumerate(self.humans)]
+            return ob, reward, done, info_from_code(code, dmin)
+        self.states.append([self.robot.get_full_state(), [h.get_full_state() for h in self.humans]])
+        if hasattr(self.robot.policy, 'action_values'):
+            self.action_values.append(self.robot.policy.action_values)
+        if hasattr(self.robot.policy, 'get_attention_weights'):
+            self.attention_weights.append(self.robot.policy.get_attention_weights())
+        eng.step(act)
         reward = float(eng.reward[0]); done = bool(eng.done[0]); code = int(eng.info[0])
         info = info_from_code(code, float(eng.dmin[0]))
-        if update:
-            self._pull()
-            for i, h in enumerate(self.humans):
-                if self.human_times[i] == 0 and h.reached_destination():
-                    self.human_times[i] = self.global_time
-            ob = [h.get_observable_state() for h in self.humans]
-        else:
-            hp, hv = s.h_pos[0].tolist(), s.h_vel[0].tolist()
-            ob = [ObservableState(hp[i][0], hp[i][1], hv[i][0], hv[i][1], h.radius) for i, h in enumerate(self.humans)]
-            for f, t in zip(s.FIELDS, snap[:-1]):
-                getattr(s, f).copy_(t)
-            s.active.copy_(snap[-1])
+        self._pull()
+        for i, h in enumerate(self.humans):
+            if self.human_times[i] == 0 and h.reached_destination():
+                self.human_times[i] = self.global_time
+        ob = [h.get_observable_state() for h in self.humans]
         return ob, reward, done, info
 
     def render(self, mode='human', output_file=None):
         raise NotImplementedError('rendering is out of scope of the CUDA path (SURVEY.md 2b)')
 
     def get_human_times(self):
-        raise NotImplementedError('centralised multi-step ORCA (crowd_sim.py:209-249) is a next row (SURVEY.md 8f row 4)')
+        """crowd_sim.py:209-249: the centralised multi-step ORCA simulation (robot + all humans) until every human has
+        reached its goal, on device (crowdsim_human_times). Like the reference it advances global_time and moves the
+        agents to where the simulation left them; the per-step `states` trace of the visualiser is not recorded."""
+        if not self.robot.reached_destination():
+            raise ValueError('Episode is not done yet')
+        eng = self._engine
+        ht, gt, fp = eng.human_times(torch.tensor([[float(t) for t in self.human_times]], dtype=torch.float64))
+        times, pos = ht[0].tolist(), fp[0].tolist()
+        if not all(times):
+            logging.warning('Simulation cannot terminate!')
+        self.human_times = times
+        self.global_time = float(gt[0])
+        self.robot.set_position(pos[0])
+        for i, h in enumerate(self.humans):
+            h.set_position(pos[i + 1])
+        return self.human_times

@@ -68,35 +68,38 @@ class ORCA(Policy):
         self._dev = None
 
     def _buffers(self, m):
-        if self._dev is None or self._dev[0] != m:
-            dev = torch.device('cuda:0')
-            z = lambda *s: torch.zeros(s, dtype=torch.float64, device=dev)  # noqa: E731
-            host = torch.zeros(8 * m + 10, dtype=torch.float64).pin_memory()
-            self._dev = (m, dict(h_pos=z(1, m, 2), h_vel=z(1, m, 2), h_goal=z(1, m, 2), h_attr=z(1, m, 2), r_pos=z(1, 2),
-                                 r_vel=z(1, 2), r_goal=z(1, 2), r_attr=z(1, 2), r_theta=z(1), g_time=z(1), out=z(1, 2)), host)
-        return self._dev[1]
+        """One device slab + one pinned staging buffer per crowd size: a predict() is ONE host->device copy, one
+        crowdsim_orca_act launch and one 16-byte read-back."""
+        dev = getattr(self, 'device', None)
+        dev = torch.device(dev) if dev is not None and torch.device(dev).type == 'cuda' else torch.device('cuda', torch.cuda.current_device())
+        if self._dev is None or self._dev[0] != (m, dev):
+            n = 8 * m + 12
+            slab = torch.zeros(n, dtype=torch.float64, device=dev)
+            off, views = 0, {}
+            for name, size in (('h_pos', 2 * m), ('h_vel', 2 * m), ('h_goal', 2 * m), ('h_attr', 2 * m), ('r_pos', 2), ('r_vel', 2),
+                               ('r_goal', 2), ('r_attr', 2), ('r_theta', 1), ('g_time', 1), ('out', 2)):
+                views[name] = slab[off:off + size]; off += size
+            self._dev = ((m, dev), views, slab, torch.zeros(n, dtype=torch.float64).pin_memory())
+        return self._dev[1], self._dev[2], self._dev[3], dev
 
     def predict(self, state):
         lib = _abi.load()
         me, others = state.self_state, state.human_states
         m = len(others)
-        d = self._buffers(m)
-        if m:
-            d['h_pos'].copy_(torch.tensor([[o.px, o.py] for o in others], dtype=torch.float64).view(1, m, 2))
-            d['h_vel'].copy_(torch.tensor([[o.vx, o.vy] for o in others], dtype=torch.float64).view(1, m, 2))
-            d['h_attr'].copy_(torch.tensor([[o.radius, 1.0] for o in others], dtype=torch.float64).view(1, m, 2))
-        d['r_pos'].copy_(torch.tensor([[me.px, me.py]], dtype=torch.float64))
-        d['r_vel'].copy_(torch.tensor([[me.vx, me.vy]], dtype=torch.float64))
-        d['r_goal'].copy_(torch.tensor([[me.gx, me.gy]], dtype=torch.float64))
-        d['r_attr'].copy_(torch.tensor([[me.radius, me.v_pref]], dtype=torch.float64))
+        d, slab, host, dev = self._buffers(m)
+        flat = [c for o in others for c in (o.px, o.py)] + [c for o in others for c in (o.vx, o.vy)] + [0.0] * (2 * m) + \
+               [c for o in others for c in (o.radius, 1.0)] + [me.px, me.py, me.vx, me.vy, me.gx, me.gy, me.radius, me.v_pref, 0.0, 0.0, 0.0, 0.0]
+        host.copy_(torch.tensor(flat, dtype=torch.float64))
         prm = _abi.Params(float(self.time_step), 25.0, 1.0, -0.25, 0.2, 0.5, float(self.neighbor_dist), float(self.time_horizon),
                           int(self.max_neighbors), 0.0, float(self.safety_space), 0, _abi.ROBOT_ORCA)
         st = _abi.State(*[d[f].data_ptr() for f in ('h_pos', 'h_vel', 'h_goal', 'h_attr', 'r_pos', 'r_vel', 'r_goal', 'r_attr',
                                                       'r_theta', 'g_time')], None)
-        rc = lib.crowdsim_orca_act(C.byref(prm), 1, m, C.byref(st), d['out'].data_ptr(),
-                                   C.c_void_p(torch.cuda.current_stream().cuda_stream))
-        _abi.check(rc, 'crowdsim_orca_act')
-        vx, vy = d['out'][0].tolist()
+        with torch.cuda.device(dev):
+            slab.copy_(host, non_blocking=True)
+            rc = lib.crowdsim_orca_act(C.byref(prm), 1, m, C.byref(st), d['out'].data_ptr(),
+                                       C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            _abi.check(rc, 'crowdsim_orca_act')
+            vx, vy = d['out'].tolist()
         self.last_state = state
         return ActionXY(vx, vy)
 

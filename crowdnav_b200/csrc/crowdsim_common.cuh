@@ -44,7 +44,7 @@ __device__ __forceinline__ void st_release_u8(uint8_t *p, uint8_t v) { asm volat
 struct KParams {
     double time_step, time_limit, success_reward, collision_penalty, discomfort_dist, discomfort_penalty_factor;
     double human_safety_space, robot_safety_space;
-    float neighbor_dist, inv_time_horizon, inv_time_step;
+    float neighbor_dist, inv_time_horizon, inv_time_step, time_step_f;
     int max_neighbors;   // semantic cap: min(orca max_neighbors, N) -- identical behaviour, a solve never sees more than N candidates
     int nb_alloc;        // shared-memory columns per thread (>= 1)
     int robot_visible, robot_policy;
@@ -60,6 +60,7 @@ inline KParams make_kparams(const crowdsim_params *p, int N)
     k.neighbor_dist = (float)p->neighbor_dist;
     k.inv_time_horizon = 1.0f / (float)p->time_horizon;      // Agent.cpp: invTimeHorizon = 1.0f / timeHorizon_
     k.inv_time_step = 1.0f / (float)p->time_step;            // invTimeStep = 1.0f / sim_->timeStep_
+    k.time_step_f = (float)p->time_step;                     // sim_->timeStep_ (Agent::update)
     k.max_neighbors = p->max_neighbors < N ? p->max_neighbors : N; if (k.max_neighbors < 0) k.max_neighbors = 0;
     k.nb_alloc = k.max_neighbors < 1 ? 1 : k.max_neighbors;
     k.robot_visible = p->robot_visible; k.robot_policy = p->robot_policy;

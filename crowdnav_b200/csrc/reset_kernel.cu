@@ -160,7 +160,7 @@ __device__ __forceinline__ bool next_seed(const crowdsim_reset_args &a, int e, u
     if (a.case_counter) {
         const int c = atomicAdd(a.case_counter, 1);
         if (c >= a.case_total) return false;
-        seed = a.seed_base + (uint32_t)c; case_id = c;
+        seed = a.seed_base + (a.case_wrap > 0 ? (uint32_t)(((long long)a.case_first + c) % a.case_wrap) : (uint32_t)c); case_id = c;
         return true;
     }
     seed = a.seed[e];

@@ -29,6 +29,10 @@ struct StepArgs {
     int has_ep, has_ar;
     int act_only;      // crowdsim_orca_act: robot lanes solve and write action_out, nothing is mutated
     int n_steps;       // crowdsim_step_n: env-steps per launch (small-crowd kernel, ORCA robot)
+    // crowdsim_onestep_lookahead (generic / crowd kernel only): step(action, update=False) -- outputs are written, the state is
+    // not; the humans' next observable states go to la_pos / la_vel instead
+    int lookahead;
+    double *la_pos, *la_vel;
 };
 
 // ---- auto-reset protocol, consumer side (include/crowdsim_b200.h: crowdsim_autoreset) ----
@@ -177,12 +181,15 @@ __global__ void __launch_bounds__(MID ? 128 : 256, MID ? CS_MID_MINBLOCKS : 1) s
 
             if (k.robot_policy == CROWDSIM_ROBOT_EXTERNAL_ROT) {                        // agent.py:133-135
                 double nth = fmod(theta + ay, 2 * CS_PI); if (nth < 0) nth += 2 * CS_PI;
-                A.st.r_theta[e] = nth; nvx = ax * cos(nth); nvy = ax * sin(nth);
+                if (!A.lookahead) A.st.r_theta[e] = nth;
+                nvx = ax * cos(nth); nvy = ax * sin(nth);
             }
-            st2(A.st.r_pos, e, make_double2(npx, npy));
-            st2(A.st.r_vel, e, make_double2(nvx, nvy));
             const double ntime = gtime + dt;
-            A.st.g_time[e] = ntime;
+            if (!A.lookahead) {
+                st2(A.st.r_pos, e, make_double2(npx, npy));
+                st2(A.st.r_vel, e, make_double2(nvx, nvy));
+                A.st.g_time[e] = ntime;
+            }
             if (A.io.action_out) st2(A.io.action_out, e, make_double2(nvx, nvy));
             A.io.reward[e] = reward; A.io.dmin[e] = dmin; A.io.done[e] = done ? 1 : 0; A.io.info[e] = (uint8_t)info;
 
@@ -227,6 +234,7 @@ __global__ void __launch_bounds__(MID ? 128 : 256, MID ? CS_MID_MINBLOCKS : 1) s
         const double hx = (double)nv.x, hy = (double)nv.y;
         const size_t i = (size_t)e * N + a;
         const double2 np_ = make_double2(pos.x + hx * dt, pos.y + hy * dt);
+        if (A.lookahead) { st2(A.la_pos, i, np_); st2(A.la_vel, i, make_double2(hx, hy)); return; }   // agent.py:63-74, nothing mutated
         st2(A.st.h_pos, i, np_);
         st2(A.st.h_vel, i, make_double2(hx, hy));
         if (A.io.obs32) reinterpret_cast<float4 *>(A.io.obs32)[i] = make_float4((float)np_.x, (float)np_.y, nv.x, nv.y);
@@ -248,7 +256,8 @@ static int sm_count()
 }
 
 static int launch(const crowdsim_params *prm, int B, int N, const crowdsim_state *st, const crowdsim_step_io *io,
-                  const crowdsim_episodes *ep, const crowdsim_autoreset *ar, int act_only, int n_steps, cudaStream_t stream)
+                  const crowdsim_episodes *ep, const crowdsim_autoreset *ar, int act_only, int n_steps, cudaStream_t stream,
+                  double *la_pos = nullptr, double *la_vel = nullptr)
 {
     if (!prm || !st || !io || B < 0 || N < 0 || n_steps < 1) return CROWDSIM_EINVAL;
     if (N > CROWDSIM_MAX_HUMANS || prm->max_neighbors > CROWDSIM_MAX_NEIGHBORS) return CROWDSIM_EUNSUPPORTED;
@@ -272,10 +281,11 @@ static int launch(const crowdsim_params *prm, int B, int N, const crowdsim_state
     if (act_only) A.k.robot_policy = CROWDSIM_ROBOT_ORCA;
     A.B = B; A.N = N; A.L = N + 1; A.EPB = envs_per_block(A.L, 128);
     A.st = *st; A.io = *io; A.has_ep = (ep != nullptr && !act_only); A.act_only = act_only; A.n_steps = 1;
+    A.lookahead = (la_pos != nullptr); A.la_pos = la_pos; A.la_vel = la_vel;
     if (A.has_ep) A.ep = *ep; else memset(&A.ep, 0, sizeof(A.ep));
     A.has_ar = (ar != nullptr && !act_only);
     if (A.has_ar) A.ar = *ar; else memset(&A.ar, 0, sizeof(A.ar));
-    if (N >= 1 && N <= 5 && !g_force_generic) {
+    if (N >= 1 && N <= 5 && !g_force_generic && !A.lookahead) {
         // small crowds: register-resident solver, 32 / (N + 1) whole envs per warp (step_flat.cuh)
         const int epb = CS_FLAT_WPB * (32 / (N + 1));
         const int blocks = (B + epb - 1) / epb;
@@ -334,6 +344,14 @@ extern "C" int crowdsim_step_n(const crowdsim_params *prm, int B, int N, crowdsi
                                crowdsim_episodes *ep, const crowdsim_autoreset *ar, int n_steps, void *stream)
 {
     return cs::launch(prm, B, N, st, io, ep, ar, 0, n_steps, (cudaStream_t)stream);
+}
+
+extern "C" int crowdsim_onestep_lookahead(const crowdsim_params *prm, int B, int N, const crowdsim_state *st, crowdsim_step_io *io,
+                                          double *next_h_pos, double *next_h_vel, void *stream)
+{
+    if (!next_h_pos || !next_h_vel || !st) return CROWDSIM_EINVAL;
+    if (io && io->obs32) return CROWDSIM_EINVAL;
+    return cs::launch(prm, B, N, st, io, nullptr, nullptr, 0, 1, (cudaStream_t)stream, next_h_pos, next_h_vel);
 }
 
 extern "C" int crowdsim_orca_act(const crowdsim_params *prm, int B, int N, const crowdsim_state *st, double *action_out,

@@ -116,9 +116,10 @@ __device__ __forceinline__ orca::V2 mid_solve(const Stage &s, const KParams &k, 
         }
         __syncthreads();
         const int cnt = *s_qcount < QC ? *s_qcount : QC;
-        for (int base = 0; base < cnt; base += kMidIPP) {
+        const int ipp = (T / SUB < kMidIPP) ? T / SUB : kMidIPP;     // whole items only: a block may have fewer than PL threads
+        for (int base = 0; base < cnt; base += ipp) {
             const int item = base + tid / SUB, i = tid % SUB + 1;
-            const bool mine = (tid < PL) && item < cnt;
+            const bool mine = (tid < ipp * SUB) && item < cnt;
             if (mine) {
                 const Lines Lq = { s_q + item, QC };
                 const int qn = __float_as_int(s_q[(4 * M + 0) * QC + item]);

@@ -126,7 +126,7 @@ class BatchedExplorer(object):
         self.target_model = copy.deepcopy(target_model)
 
     def run_k_episodes(self, k, phase, update_memory=False, imitation_learning=False, episode=None,
-                       print_failure=False, prefetch_every=2, check_every=32):
+                       print_failure=False, prefetch_every=2, check_every=32, steps_per_launch=8):
         env = self.env
         if update_memory and (self.memory is None or self.gamma is None):
             raise ValueError('Memory or gamma value is not set!')            # explorer.py:93-94
@@ -135,7 +135,7 @@ class BatchedExplorer(object):
         gamma = self.gamma if self.gamma is not None else 0.9
         ep = env.track_episodes(max(n_local, 1), gamma)
         rule = env.test_sim if phase == 'test' else env.train_val_sim
-        env.set_case_queue((first_case + start) % env.case_size[phase], n_local, phase)
+        env.set_case_queue((first_case + start) % env.case_size[phase], n_local, phase)    # wraps inside the phase like crowd_sim.py:283
         env.enable_autoreset(rule)
         if self.robot_policy == 'orca':
             env.set_robot_policy('orca')
@@ -149,6 +149,13 @@ class BatchedExplorer(object):
             recorder = TrajectoryRecorder(env, self.memory, self.gamma, imitation_learning, self.target_model, om=om)
         side = torch.cuda.Stream(device=env.device)
         main = torch.cuda.current_stream(env.device)
+        # an ORCA robot decides on device: the episode loop of explorer.py:41-43 closes inside the kernel, several steps per
+        # launch (crowdsim_step_n); a recorded rollout or a host-side policy needs every step
+        chunk = max(1, int(steps_per_launch)) if (self.robot_policy == 'orca' and recorder is None) else 1
+        if chunk > 1:
+            prefetch_every, check_every = 1, max(1, check_every // chunk)
+        from .batched import max_episode_steps
+        guard = 2 * (max_episode_steps(env.time_limit, env.time_step) + chunk) * (n_local // max(env.B, 1) + 2) // chunk + 16
         it = 0
         while True:
             if it % prefetch_every == 0:
@@ -158,7 +165,7 @@ class BatchedExplorer(object):
             if recorder is not None:
                 recorder.before_step()
             if self.robot_policy == 'orca':
-                env.step()
+                env.step(n_steps=chunk)
             else:
                 env.step(self.robot_policy.act_batch(env))
             if recorder is not None:
@@ -166,7 +173,7 @@ class BatchedExplorer(object):
             it += 1
             if it % check_every == 0 and int(env.state.active.sum()) == 0 and int(env.autoreset.want.sum()) == 0:
                 break
-            if it > 200 * (n_local // max(env.B, 1) + 2):
+            if it > guard:
                 raise RuntimeError('rollout did not terminate')
         main.wait_stream(side)
         rows = gather_results(pack_results(ep, n_local), k, self.rank, self.world, self.group)

@@ -52,7 +52,7 @@ class DeviceReplayMemory(object):
 
 
 class TrajectoryRecorder(object):
-    def __init__(self, env, memory, gamma, imitation_learning=True, target_model=None, max_steps=128, om=None):
+    def __init__(self, env, memory, gamma, imitation_learning=True, target_model=None, max_steps=None, om=None):
         """om = None or (cell_num, cell_size, om_channel_size): append the occupancy maps of the current human states to
         every recorded row, as MultiHumanRL.transform does with with_om (multi_human_rl.py:98-104)."""
         self.env, self.memory = env, memory
@@ -60,7 +60,8 @@ class TrajectoryRecorder(object):
         F = 13 + (om[0] * om[0] * om[2] if om else 0)
         self.il, self.target_model = imitation_learning, target_model
         B, N, dev = env.B, env.human_num, env.device
-        self.T = max_steps
+        from .batched import max_episode_steps
+        self.T = max_steps or max(128, max_episode_steps(env.time_limit, env.time_step))     # covers the longest episode
         self.states = torch.zeros((B, self.T, N, F), dtype=torch.float32, device=dev)
         self.rewards = torch.zeros((B, self.T), dtype=torch.float64, device=dev)
         self.returns = torch.zeros((B, self.T), dtype=torch.float64, device=dev)

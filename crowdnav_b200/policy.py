@@ -116,7 +116,12 @@ class LSTMRLValueNetwork(nn.Module):
 
 
 class BatchedValuePolicy(object):
-    """Greedy one-step-lookahead policy over a value network (test / val phase of MultiHumanRL.predict and CADRL.predict).
+    """One-step-lookahead policy over a value network (MultiHumanRL.predict / CADRL.predict): greedy in the test / val
+    phases, epsilon-greedy in the train phase (multi_human_rl.py:27-31, cadrl.py:148-152: with probability epsilon a
+    uniformly drawn action of the 81-action space). The reference draws from numpy's GLOBAL generator (re-seeded by every
+    env.reset, shared with scenario generation); here every env has its own uniform draw from a torch.Generator on the
+    policy's device (set_seed): same distribution, a different random stream -- RL-phase rollouts are statistically, not
+    bitwise, reproductions of the reference's.
 
     act_batch(env) -> [B][2] float64 device tensor with, per env,
         argmax_a  reward(s, a) + gamma ** (time_step * v_pref) * V(rotate(next_state(s, a)))       multi_human_rl.py:52
@@ -143,7 +148,10 @@ class BatchedValuePolicy(object):
         self.actions = None
         self.device = None
         self.phase = 'test'
+        self.epsilon = 0.0                   # train.py:148-152 sets it every episode (policy.set_epsilon)
+        self._gen = None; self._seed = 0
         self.action_values = None
+        self.explored = None                 # [B] bool: which envs took a random action in the last act_batch (train phase)
         self._buf_states = None; self._buf_reward = None
 
     def set_device(self, device):
@@ -153,6 +161,14 @@ class BatchedValuePolicy(object):
 
     def set_phase(self, phase):
         self.phase = phase
+
+    def set_epsilon(self, epsilon):
+        """policy.py:37-38"""
+        self.epsilon = float(epsilon)
+
+    def set_seed(self, seed):
+        """Seed of the exploration draws (per-env uniforms + action indices)."""
+        self._seed = int(seed); self._gen = None
 
     def get_model(self):
         return self.model
@@ -167,7 +183,9 @@ class BatchedValuePolicy(object):
             self._buf_states = torch.empty((B, A, N, 13), dtype=torch.float32, device=self.device)
             self._buf_reward = torch.empty((B, A), dtype=torch.float64, device=self.device)
         states, reward = env.lookahead_pack(self.actions, out_states=self._buf_states, out_reward=self._buf_reward)
-        discount = pow(self.gamma, self.time_step * self.v_pref)
+        # multi_human_rl.py:52: pow(gamma, time_step * state.self_state.v_pref) -- the robot's v_pref of THIS env
+        discount = torch.pow(torch.full((B,), float(self.gamma), dtype=torch.float64, device=self.device),
+                             self.time_step * env.state.r_attr[:, 1]).unsqueeze(1)
         F = 13
         if self.with_om:
             npos, nvel = env.lookahead_humans()
@@ -181,6 +199,14 @@ class BatchedValuePolicy(object):
         values = reward + discount * v.double()                        # python-float arithmetic in the reference
         self.action_values = values
         best = values.argmax(dim=1)
+        self.explored = None
+        if self.phase == 'train' and self.epsilon > 0.0:                # epsilon-greedy (multi_human_rl.py:27-31)
+            if self._gen is None:
+                self._gen = torch.Generator(device=self.device); self._gen.manual_seed(self._seed)
+            u = torch.rand((B,), generator=self._gen, device=self.device, dtype=torch.float64)
+            rnd = torch.randint(0, A, (B,), generator=self._gen, device=self.device)
+            self.explored = u < self.epsilon
+            best = torch.where(self.explored, rnd, best)
         act = self.actions[best]
         s = env.state                                                  # policy.py:41-48 reach_destination
         dy, dx = s.r_pos[:, 1] - s.r_goal[:, 1], s.r_pos[:, 0] - s.r_goal[:, 0]

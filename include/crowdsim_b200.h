@@ -25,6 +25,8 @@
  *   crowdsim_pack_joint      crowd_sim/envs/utils/state.py:17-18,36-37 (14-tuple) + cadrl.py:187-222 (rotate)
  *   crowdsim_lookahead_humans  the observation of env.onestep_lookahead (crowd_sim.py:314-315,414-416; agent.py:63-74)
  *   crowdsim_occupancy_maps  crowd_nav/policy/multi_human_rl.py:109-163 (MultiHumanRL.build_occupancy_maps)
+ *   crowdsim_onestep_lookahead  crowd_sim/envs/crowd_sim.py:314-315 (step(action, update=False)), one action per env
+ *   crowdsim_human_times     crowd_sim/envs/crowd_sim.py:209-249 (CrowdSim.get_human_times: the centralised multi-step sim)
  *
  * Layout in HBM (structure of arrays, float64 like the reference's Python floats):
  *   two-vectors are interleaved (x,y) pairs so one agent's pair is one 16-byte load;
@@ -185,11 +187,17 @@ typedef struct crowdsim_reset_args {
     double discomfort_dist;  /* 0.2 (min initial separation, crowd_sim.py:168) */
     int32_t randomize_attributes; /* env.config [env] randomize_attributes (agent.py:39-45) */
     /* Optional case work-queue (Explorer.run_k_episodes over k cases with fewer slots): when case_counter != NULL the
-     * seed of a generated scene is seed_base + c with c = atomicAdd(case_counter, 1); c >= case_total => no scene
+     * seed of a generated scene is seed_base + c (see case_wrap below) with c = atomicAdd(case_counter, 1); c >= case_total => no scene
      * (prefetch marks the slot EXHAUSTED). `seed`/`seed_stride` are ignored then. */
     int32_t *case_counter;
     int32_t case_total;
     uint32_t seed_base;
+    /* Wrap of the case numbers inside a phase (crowd_sim.py:283: case_counter = (case_counter + 1) % case_size): when
+     * case_wrap > 0 the seed of queue entry c is seed_base + (case_first + c) % case_wrap, i.e. seed_base = offset[phase]
+     * and the k cases of a run that crosses the end of the phase's case range continue at case 0 like the reference's;
+     * case_wrap = 0: seed_base + c. */
+    int32_t case_first;
+    int32_t case_wrap;
 } crowdsim_reset_args;
 
 /* Library / device probing (host only, no kernel launch). */
@@ -273,6 +281,27 @@ int crowdsim_lookahead_humans(const crowdsim_params *prm, int B, int N, const cr
  */
 int crowdsim_occupancy_maps(int B, int N, const double *h_pos, const double *h_vel, int cell_num, double cell_size,
                             int channels, float *out, void *stream);
+
+/*
+ * env.onestep_lookahead(action) = step(action, update=False) (crowd_sim/envs/crowd_sim.py:314-315, 414-416) for one robot
+ * action PER ENV: io->reward / dmin / done / info (and action_out) are those step() would return, next_h_pos / next_h_vel
+ * [B][N][2] the humans' next observable states (agent.py:63-74); state, time and bookkeeping are NOT modified (the env must be
+ * active). For the 81-action sweep of the value-network policies use crowdsim_lookahead_pack.
+ */
+int crowdsim_onestep_lookahead(const crowdsim_params *prm, int B, int N, const crowdsim_state *st, crowdsim_step_io *io,
+                               double *next_h_pos, double *next_h_vel, void *stream);
+
+/*
+ * CrowdSim.get_human_times (crowd_sim/envs/crowd_sim.py:209-249): from the CURRENT state (an episode the robot has finished
+ * at its goal) one centralised ORCA simulation of the robot and all N humans -- every agent solves from the same pre-state,
+ * radius = the plain agent radius, positions advance in float32 like rvo2's own -- is stepped until every human has reached
+ * its goal (at most max_steps steps). human_times [B][N] float64 in/out: entries that are already non-zero (humans that
+ * arrived during the episode, crowd_sim.py:404-407) are kept, the others receive the global_time of their arrival (0 if
+ * max_steps ran out). g_time_out [B]: env.global_time afterwards. final_pos [B][N+1][2] or NULL: the agents' final
+ * positions, robot first. The state arrays are NOT modified. N >= 1.
+ */
+int crowdsim_human_times(const crowdsim_params *prm, int B, int N, const crowdsim_state *st, double *human_times,
+                         double *g_time_out, double *final_pos, int max_steps, void *stream);
 
 #ifdef __cplusplus
 }

@@ -93,7 +93,7 @@ static int next_seed(const crowdsim_reset_args *a, int e, uint32_t *seed, int *c
         #pragma omp atomic capture
         c = (*a->case_counter)++;
         if (c >= a->case_total) return 0;
-        *seed = a->seed_base + (uint32_t)c; *case_id = c;
+        *seed = a->seed_base + (a->case_wrap > 0 ? (uint32_t)(((long long)a->case_first + c) % a->case_wrap) : (uint32_t)c); *case_id = c;
         return 1;
     }
     *seed = a->seed[e];

@@ -357,7 +357,89 @@ def run_policy_decisions():
         json.dump(out, f, separators=(',', ':'))
 
 
+def run_rl_memory():
+    """Explorer.update_memory in RL mode (explorer.py:107-113), the reference's own method: value = reward +
+    gamma^(dt v_pref) * target_model(next state), the reward alone on the terminal step, for every step of the episodes that
+    end in success or collision (explorer.py:66-69). The episodes are the ORCA robot's test cases 0..7; the stored states are
+    MultiHumanRL.transform(JointState) of a SARL policy (seed-0 weights, policy.config defaults) whose network is also the
+    target model. (A randomly initialised SARL robot never ends an episode other than by timeout -- 40 of 40 train cases --
+    and timeouts are not stored, so the robot that moves is ORCA; update_memory itself is called exactly as run_k_episodes
+    calls it.)"""
+    pcfg = configparser.RawConfigParser()
+    pcfg.read(os.path.join(REF, 'crowd_nav', 'configs', 'policy.config'))
+    torch.manual_seed(0)
+    sarl = policy_factory['sarl'](); sarl.configure(pcfg); sarl.set_device(torch.device('cpu')); sarl.set_phase('test')
+    env, robot, _ = make_env(human_num=5, test_sim='circle_crossing')
+
+    class ListMemory(list):
+        def push(self, item):
+            self.append(item)
+    mem = ListMemory()
+    gamma = sarl.gamma
+    explorer = Explorer(env, robot, torch.device('cpu'), memory=mem, gamma=gamma, target_policy=sarl)
+    explorer.update_target_model(sarl.get_model())
+    episodes = []
+    for case in range(8):
+        ob = env.reset('test', case)
+        states, rewards, done = [], [], False
+        while not done:
+            states.append(sarl.transform(JointState(robot.get_full_state(), ob)))
+            ob, reward, done, info = env.step(robot.act(ob))
+            rewards.append(reward)
+        n0 = len(mem)
+        if isinstance(info, (ReachGoal, Collision)):
+            explorer.update_memory(states, None, rewards, imitation_learning=False)
+        episodes.append({'case': case, 'info': INFO_CODE[type(info)], 'steps': len(rewards), 'stored': len(mem) - n0})
+    out = {'seed': 0, 'gamma': gamma, 'episodes': episodes, 'pairs': len(mem),
+           'values': [R(v.item()) for _, v in mem],
+           'states': [[[R(x) for x in row] for row in st.tolist()] for st, _ in mem]}
+    print('rl_memory pairs', len(mem), [(e['case'], e['info'], e['stored']) for e in episodes])
+    with gzip.open(os.path.join(OUT, 'rl_update_memory.json.gz'), 'wt') as f:
+        json.dump(out, f, separators=(',', ':'))
+
+
+def run_human_times():
+    """CrowdSim.get_human_times (crowd_sim.py:209-249) of the reference itself, after ORCA-robot episodes that ended at the
+    goal: the state the call starts from, the arrivals already recorded during the episode, and what the call returns /
+    leaves behind (human_times, global_time, agent positions)."""
+    rows = []
+    for tag, kw, cases in (('circle5', dict(human_num=5, test_sim='circle_crossing'), range(0, 40)),
+                           ('circle10_visible', dict(human_num=10, test_sim='circle_crossing', robot_visible=True), range(0, 6)),
+                           ('square20', dict(human_num=20, test_sim='square_crossing'), range(0, 30))):
+        env, robot, _ = make_env(**kw)
+        got = 0
+        for case in cases:
+            ob = env.reset('test', case)
+            done = False
+            while not done:
+                ob, reward, done, info = env.step(robot.act(ob))
+            if not isinstance(info, ReachGoal) or not robot.reached_destination():
+                continue
+            pre = scene(env)
+            before = [R(t) for t in env.human_times]
+            t0 = env.global_time
+            times = env.get_human_times()
+            rows.append({'tag': tag, 'case': case, 'N': kw['human_num'], 'robot_visible': bool(kw.get('robot_visible', False)),
+                         'scene': pre, 'global_time': R(t0), 'human_times_before': before,
+                         'human_times': [R(t) for t in times], 'global_time_after': R(env.global_time),
+                         'final_robot': [R(robot.px), R(robot.py)], 'final_humans': [[R(h.px), R(h.py)] for h in env.humans]})
+            got += 1
+            if got >= (6 if tag == 'circle5' else 3):
+                break
+        print('human_times', tag, got)
+    with gzip.open(os.path.join(OUT, 'human_times.json.gz'), 'wt') as f:
+        json.dump({'rows': rows}, f, separators=(',', ':'))
+
+
 def main():
+    if '--human-times-only' in sys.argv:
+        os.makedirs(OUT, exist_ok=True)
+        run_human_times()
+        return
+    if '--rl-memory-only' in sys.argv:
+        os.makedirs(OUT, exist_ok=True)
+        run_rl_memory()
+        return
     if '--policies-only' in sys.argv:
         os.makedirs(OUT, exist_ok=True)
         run_policy_decisions()
@@ -393,6 +475,8 @@ def main():
     run_rotate()
     run_om()
     run_policy_decisions()
+    run_rl_memory()
+    run_human_times()
 
 
 if __name__ == '__main__':

@@ -137,10 +137,10 @@ class HostAutoReset(object):
 
 
 def _reset_args(seeds, rule, mask, circle_radius, square_width, human_radius, human_v_pref, robot_radius, robot_v_pref,
-                discomfort_dist, randomize_attributes, seed_stride, case_counter, case_total, seed_base):
+                discomfort_dist, randomize_attributes, seed_stride, case_counter, case_total, seed_base, case_first=0, case_wrap=0):
     return _abi.ResetArgs(_ptr(mask), _ptr(seeds), int(seed_stride), _abi.RULES[rule], circle_radius, square_width,
                           human_radius, human_v_pref, robot_radius, robot_v_pref, discomfort_dist,
-                          int(randomize_attributes), _ptr(case_counter), int(case_total), int(seed_base))
+                          int(randomize_attributes), _ptr(case_counter), int(case_total), int(seed_base), int(case_first), int(case_wrap))
 
 
 def prefetch(ar, B, N, seeds=None, rule='circle_crossing', circle_radius=4.0, square_width=10.0, human_radius=0.3,

@@ -496,6 +496,60 @@ def test_step_n_generic_and_external_fall_back_to_launch_loops(cuda_env, oracle)
         _assert_io_equal(env, io, what='step_n fallback N=%d' % N)
 
 
+def test_human_times_match_reference(cuda_env, oracle):
+    """crowdsim_human_times against the reference's own CrowdSim.get_human_times (tests/golden/human_times: run after ORCA-robot
+    episodes that ended at the goal; 5, 10 and 20 humans): arrival times, final global_time and the final positions of all
+    agents -- the centralised float32 simulation is reproduced bit for bit; the live state is not touched."""
+    rows = load_golden('human_times')['rows']
+    assert len(rows) >= 10
+    for r in rows:
+        N = r['N']
+        host = fill_host_state(oracle, [r['scene']], N)
+        host.g_time[:] = float(r['global_time'])
+        env = cuda_env(1, N, robot_visible=r['robot_visible'])
+        env.state.load_host(host)
+        before = torch.tensor([[float(t) for t in r['human_times_before']]], dtype=torch.float64)
+        ht, gt, fp = env.human_times(before)
+        torch.cuda.synchronize()
+        assert ht[0].tolist() == [float(t) for t in r['human_times']], (r['tag'], r['case'])
+        assert float(gt[0]) == float(r['global_time_after'])
+        want = np.array([[float(x) for x in r['final_robot']]] + [[float(x) for x in h] for h in r['final_humans']])
+        assert np.array_equal(fp[0].cpu().numpy(), want), (r['tag'], r['case'])
+        _assert_state_equal(env, host, what='human_times leaves the state alone')
+
+
+@pytest.mark.parametrize('N,vis,policy', [(5, 0, 'external_xy'), (5, 1, 'external_xy'), (3, 1, 'external_rot'), (12, 1, 'external_xy')])
+def test_onestep_lookahead_is_a_step_without_update(cuda_env, oracle, N, vis, policy):
+    """crowdsim_onestep_lookahead = step(action, update=False) (crowd_sim.py:314-315, 414-416): reward / dmin / done / info of
+    the step that would happen, the humans' next observable states, and NOTHING mutated -- checked against one oracle step on
+    a copy of the state."""
+    from crowdnav_b200 import _abi
+    B = 600
+    host = _random_host_state(oracle, B, N, seed=60 + N)
+    env = cuda_env(B, N, robot_visible=bool(vis), robot_policy=policy)
+    env.state.load_host(host)
+    pol = {'external_xy': _abi.ROBOT_EXTERNAL_XY, 'external_rot': _abi.ROBOT_EXTERNAL_ROT}[policy]
+    prm = oracle.default_params(robot_visible=vis, robot_policy=pol)
+    io = oracle.HostStepIO(B)
+    rng = np.random.RandomState(8)
+    if policy == 'external_rot':
+        io.action[:, 0] = rng.uniform(0, 1, B); io.action[:, 1] = rng.uniform(-0.8, 0.8, B)
+    else:
+        io.action[...] = rng.uniform(-1, 1, (B, 2))
+    (npos, nvel, _), rew, done, info = env.onestep_lookahead(torch.from_numpy(io.action).to(env.device))
+    torch.cuda.synchronize()
+    _assert_state_equal(env, host, what='lookahead leaves the state alone')
+    import copy
+    stepped = copy.deepcopy(host)
+    oracle.step(prm, stepped, io)
+    assert np.array_equal(npos.cpu().numpy(), stepped.h_pos) and np.array_equal(nvel.cpu().numpy(), stepped.h_vel)
+    assert np.array_equal(info.cpu().numpy(), io.info) and np.array_equal(done.cpu().numpy(), io.done)
+    if policy == 'external_rot':
+        assert np.allclose(rew.cpu().numpy(), io.reward, rtol=0, atol=1e-12)
+    else:
+        assert np.array_equal(rew.cpu().numpy(), io.reward) and np.array_equal(env.dmin.cpu().numpy(), io.dmin)
+
+
 def test_lookahead_humans_matches_oracle(cuda_env, oracle):
     """crowdsim_lookahead_humans = the `ob` of env.onestep_lookahead (crowd_sim.py:414-416): bit-exact against one oracle
     step on a copy of the state, small and large crowds, robot visible or not; the live state is untouched."""

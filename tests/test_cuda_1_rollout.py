@@ -151,6 +151,48 @@ def test_update_memory_matches_single_env_explorer(cuda_env):
     assert (mem.states[:len(mem)].cpu() - ref_states).abs().max() < 2e-5
 
 
+def test_rl_update_memory_matches_reference_fixture(cuda_env):
+    """Explorer.update_memory in RL mode (explorer.py:107-113) against pairs produced by the REFERENCE's own method
+    (tests/golden/rl_update_memory, oracle/gen_golden.py: run_rl_memory): ORCA-robot test cases 0..7 through one slot, target
+    network = SARL with seed-0 weights; stored states = rotate(joint state), value = reward + gamma^(dt v_pref) *
+    target(next state), the reward alone on terminal steps; timeouts are not stored."""
+    from crowdnav_b200.explorer import BatchedExplorer
+    from crowdnav_b200.memory import DeviceReplayMemory
+    from crowdnav_b200.policy import make_sarl
+    d = load_golden('rl_update_memory')
+    env = cuda_env(1, 5)
+    target = make_sarl(gamma=d['gamma'], seed=d['seed'])
+    target.set_device(env.device)
+    mem = DeviceReplayMemory(4096, 5, env.device)
+    ex = BatchedExplorer(env, 'orca', memory=mem, gamma=d['gamma'])
+    ex.update_target_model(target.get_model())
+    ex.run_k_episodes(len(d['episodes']), 'test', update_memory=True, imitation_learning=False, check_every=1)
+    assert len(mem) == d['pairs'] == sum(e['stored'] for e in d['episodes'])
+    ref_values = torch.tensor([float(v) for v in d['values']], dtype=torch.float32)
+    ref_states = torch.tensor([[[float(x) for x in row] for row in st] for st in d['states']], dtype=torch.float32)
+    assert (mem.states[:len(mem)].cpu() - ref_states).abs().max() < 2e-5
+    assert (mem.values[:len(mem), 0].cpu() - ref_values).abs().max() < 1e-5
+    # terminal steps carry the bare reward: 1 for ReachGoal, -0.25 for Collision
+    ends = torch.tensor([e['stored'] for e in d['episodes']]).cumsum(0) - 1
+    assert [float(v) for v in mem.values[ends.to(mem.values.device), 0].cpu()] == [1.0 if e['info'] == 2 else -0.25 for e in d['episodes']]
+
+
+def test_explorer_case_range_wraps_like_the_reference(cuda_env):
+    """crowd_sim.py:283: case_counter wraps modulo case_size. A run of 30 test cases that starts at case 485 covers cases
+    485..499 and then 0..14 -- on device through the case queue (crowdsim_reset_args.case_first / case_wrap)."""
+    from crowdnav_b200.explorer import BatchedExplorer
+    cases = load_golden('suite_circle5_invisible')['cases']
+    env = cuda_env(64, 5)
+    env.case_counter['test'] = 485
+    ex = BatchedExplorer(env, 'orca', gamma=0.9)
+    ex.run_k_episodes(30, 'test')
+    want = [cases[(485 + i) % 500] for i in range(30)]
+    rows = ex.last_rows.cpu().tolist()
+    assert [int(r[0]) for r in rows] == [c['info'] for c in want]
+    assert [int(r[1]) for r in rows] == [c['steps'] for c in want]
+    assert env.case_counter['test'] == 15
+
+
 @pytest.mark.parametrize('obs,N', [('f64', 5), ('f32', 5), ('f32', 8)])
 def test_host_stepper_matches_oracle(cuda_env, oracle, obs, N):
     """The host-facing step API (pinned buffers in/out, one CUDA graph per call): driving the robot from the host with the

@@ -76,6 +76,24 @@ def test_step_and_lookahead_semantics():
     assert done and str(info) == 'Reaching goal' and abs(env.global_time - 0.25 * len(d)) < 1e-12
 
 
+def test_get_human_times_through_the_single_env_surface():
+    """env.get_human_times() (crowd_sim.py:209-249) after an episode the ORCA robot finished at its goal: the reference's
+    recorded arrival times; raises like the reference while the robot is not at its goal."""
+    r = [x for x in load_golden('human_times')['rows'] if x['tag'] == 'circle5'][0]
+    env, robot = _make()
+    ob = env.reset('test', r['case'])
+    with pytest.raises(ValueError):
+        env.get_human_times()
+    done = False
+    while not done:
+        ob, reward, done, info = env.step(robot.act(ob))
+    assert str(info) == 'Reaching goal'
+    assert [float(t) for t in env.human_times] == [float(t) for t in r['human_times_before']]
+    times = env.get_human_times()
+    assert times == [float(t) for t in r['human_times']] and env.global_time == float(r['global_time_after'])
+    assert abs(robot.px - float(r['final_robot'][0])) < 1e-6 and abs(env.humans[2].py - float(r['final_humans'][2][1])) < 1e-6
+
+
 def test_debug_scene_minus_one():
     env, robot = _make()
     ob = env.reset('test', -1)          # crowd_sim.py:286-292

@@ -429,6 +429,47 @@ def _oracle_backed_env(oracle, rows):
     return Env()
 
 
+def test_epsilon_greedy_and_per_env_discount(oracle):
+    """Train-phase predict (multi_human_rl.py:27-31): with probability epsilon a uniformly drawn action of the 81-action
+    space, per env; greedy otherwise and always in the val / test phases. The discount of the one-step value uses the
+    robot's v_pref of THAT env (multi_human_rl.py:52: pow(gamma, time_step * state.self_state.v_pref))."""
+    from crowdnav_b200.policy import make_cadrl
+    rows = load_golden('policy_decisions')['cadrl']['decisions'] * 40          # 360 envs
+    env = _oracle_backed_env(oracle, rows)
+    B = env.B
+    pol = make_cadrl(gamma=0.9, seed=0)
+    greedy = pol.act_batch(env).clone()
+    assert pol.explored is None
+    pol.set_phase('train'); pol.set_seed(3)
+    pol.set_epsilon(0.0)
+    assert torch.equal(pol.act_batch(env), greedy) and pol.explored is None
+    pol.set_epsilon(1.0)
+    a1 = pol.act_batch(env)
+    assert bool(pol.explored.all())
+    space = torch.from_numpy(pol.action_space_np)
+    assert all(bool((space == a1[e]).all(dim=1).any()) for e in range(B))       # every action is one of the 81
+    assert len({tuple(x) for x in a1.tolist()}) > 40                             # drawn per env, not one draw for the batch
+    pol.set_epsilon(0.3)
+    pol.act_batch(env)
+    frac = float(pol.explored.double().mean())
+    assert 0.2 < frac < 0.4
+    keep = ~pol.explored
+    assert torch.equal(pol.act_batch(env)[keep & ~pol.explored], greedy[keep & ~pol.explored])
+    pol.set_phase('val')
+    assert torch.equal(pol.act_batch(env), greedy) and pol.explored is None
+    # per-env v_pref in the discount
+    pol.set_phase('test')
+    v0 = pol.action_values.clone()
+    env.state.r_attr[:, 1] = torch.linspace(0.5, 1.5, B, dtype=torch.float64)
+    pol.act_batch(env)
+    s, r = env.lookahead_pack(pol.actions)
+    vnet = pol.model(s.view(B * 81 * 5, 13)).view(B, 81, 5).min(dim=2).values.double()
+    for e in (0, B // 2, B - 1):
+        want = r[e] + pow(0.9, 0.25 * float(env.state.r_attr[e, 1])) * vnet[e]
+        assert (pol.action_values[e] - want).abs().max() < 1e-12
+    assert not torch.allclose(pol.action_values, v0)
+
+
 @pytest.mark.parametrize('key', ['cadrl', 'lstm_rl', 'lstm_rl_interaction'])
 def test_cadrl_and_lstm_rl_policy_logic_matches_reference(oracle, key):
     """BatchedValuePolicy for CADRL (min over the per-human values, cadrl.py:163-166) and LSTM-RL (with query_env the
