@@ -464,7 +464,7 @@ def run_ours(args):
         return float(tq.item())
     n_ch = 4
     one = [envs[0]]
-    g_same, f_same = stream_graph(0, [0], n_chunks=n_ch), stream_graph(0, [0], step_fn=refill, side=True)
+    g_same, f_same = stream_graph(0, [0], n_chunks=n_ch), stream_graph(0, [0], n_chunks=n_ch, step_fn=refill, side=True)   # one refill per step launch
     reps = max(3, int(0.03 / (n_ch * C * 8e-6)))
     time_pair(g_same, f_same, 2)
     b0 = env_steps_done(one)
@@ -586,8 +586,26 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return world * B * n * len(group) / float(t.item())
 
+    from crowdnav_b200.batched import HostStepperGroup
+    group = HostStepperGroup(steppers)
+
+    def e2e_native(n):
+        """The same round-robin with the loop in native code (HostStepperGroup.run = crowdsim_host_pump): wait, hand the
+        device's decision back as the next action (host memcpy), launch -- per batch-step, for every batch."""
+        group.start()
+        barrier()
+        t0 = time.perf_counter()
+        group.run(n)
+        group.wait()
+        dt_ = time.perf_counter() - t0
+        t = torch.tensor([dt_], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return world * B * n * len(steppers) / float(t.item())
+
     e2e_single = e2e_rate(steppers[:1], ke)                  # one batch, host blocks on every step (the reference's loop shape)
-    e2e_value = sorted(e2e_rate(steppers, ke) for _ in range(3))[1] if P > 1 else e2e_single  # P independent batches in flight, median of 3
+    e2e_python = sorted(e2e_rate(steppers, ke) for _ in range(3))[1] if P > 1 else e2e_single  # P batches in flight, Python round-robin, median of 3
+    e2e_value = sorted(e2e_native(2 * ke) for _ in range(3))[1]                                # the same, round-robin in native code
     stepper = steppers[0]
     h2d, d2h = stepper.h2d_bytes, stepper.d2h_bytes
     launches_note = 'timed region: %d rounds x (%d crowdsim_step_n launches of %d env-steps + %d scene-prefetch launches); per round every stream replays its graph of step launches and every side stream its graph of refills' % (rounds, pools, C, pools)
@@ -633,8 +651,8 @@ def run_ours(args):
                               'note': 'value = performed / time; performed is counted by the step kernel (episode step counters), nominal = envs x steps; they differ only if envs waited for a scene refill'},
                 'clocks': clocks, 'gpu_launches': int(launches), 'gpu_launches_note': launches_note,
                 'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                        'steps': ke, 'batches_in_flight': P, 'single_batch_blocking': e2e_single, 'observation': args.e2e_obs,
-                        'note': 'HostStepper.launch()/wait() round-robin over %d independent %d-env batches: per batch-step a pinned host action buffer goes up and obs (%s)/reward/dmin/done/info/next ORCA action come down (byte counts are per batch-step), the host waits for a batch\'s results before it feeds that batch again; single_batch_blocking = one batch, host blocks on every step' % (P, B, 'float32 px,py,vx,vy per human' if args.e2e_obs == 'f32' else 'float64 state arrays')},
+                        'steps': 2 * ke, 'batches_in_flight': P, 'single_batch_blocking': e2e_single, 'python_round_robin': e2e_python, 'observation': args.e2e_obs,
+                        'note': 'HostStepperGroup.run() (round-robin in native code: crowdsim_host_pump; python_round_robin = the same loop written in Python with HostStepper.launch()/wait()) over %d independent %d-env batches: per batch-step a pinned host action buffer goes up and obs (%s)/reward/dmin/done/info/next ORCA action come down (byte counts are per batch-step), the host waits for a batch\'s results before it feeds that batch again; single_batch_blocking = one batch, host blocks on every step' % (P, B, 'float32 px,py,vx,vy per human' if args.e2e_obs == 'f32' else 'float64 state arrays')},
                 'single_batch': single, 'parity_500_cases': parity, 'episodes': episodes, 'roofline': roofline, 'scale': scale, 'cpu_baseline': cpu}
         print(json.dumps(line))
     if world > 1:

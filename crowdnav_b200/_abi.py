@@ -91,7 +91,7 @@ def declare(lib, prefix='crowdsim_', with_stream=True):
 
 
 EXPORTS = ('crowdsim_abi_version', 'crowdsim_device_check', 'crowdsim_launch_count', 'crowdsim_debug_force_generic', 'crowdsim_graph_launch',
-           'crowdsim_event_wait', 'crowdsim_step', 'crowdsim_step_n',
+           'crowdsim_event_wait', 'crowdsim_host_pump', 'crowdsim_step', 'crowdsim_step_n',
            'crowdsim_orca_act', 'crowdsim_reset', 'crowdsim_prefetch_scenes', 'crowdsim_pack_joint', 'crowdsim_lookahead_pack',
            'crowdsim_lookahead_humans', 'crowdsim_occupancy_maps', 'crowdsim_human_times', 'crowdsim_onestep_lookahead')
 
@@ -125,6 +125,8 @@ def load():
         lib.crowdsim_graph_launch.restype = C.c_int
         lib.crowdsim_event_wait.argtypes = [C.c_void_p]
         lib.crowdsim_event_wait.restype = C.c_int
+        lib.crowdsim_host_pump.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+        lib.crowdsim_host_pump.restype = C.c_int
         lib.crowdsim_lookahead_humans.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.POINTER(State), C.c_void_p, C.c_void_p, C.c_void_p]
         lib.crowdsim_lookahead_humans.restype = C.c_int
         lib.crowdsim_occupancy_maps.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]

@@ -531,6 +531,39 @@ class HostStepper(object):
         return self._result
 
 
+class HostStepperGroup(object):
+    """Several independent env batches kept in flight from the host, with the round-robin itself in native code
+    (crowdsim_host_pump): per batch-step wait for the batch's results, hand the device's next decision back as the action
+    (replay mode: h_next_action -> h_action; a caller with its own policy uses HostStepper.launch / wait instead and writes
+    h_action itself), enqueue the next step. Every batch-step still pays its H2D action copy and D2H result copy."""
+
+    def __init__(self, steppers, replay_next_action=True):
+        self.steppers = list(steppers)
+        n = len(self.steppers)
+        arr = lambda vals: (C.c_void_p * n)(*vals)  # noqa: E731
+        self._execs = arr([s._exec for s in self.steppers])
+        self._streams = arr([s._stream_h for s in self.steppers])
+        self._events = arr([s._event_h for s in self.steppers])
+        self._dst = arr([s.h_action.data_ptr() for s in self.steppers]) if replay_next_action else None
+        self._src = arr([s.h_next_action.data_ptr() for s in self.steppers]) if replay_next_action else None
+        self._bytes = self.steppers[0].h_action.numel() * 8 if replay_next_action else 0
+        self._lib = _abi.load()
+
+    def start(self):
+        for s in self.steppers:
+            s.launch()
+
+    def run(self, rounds):
+        """`rounds` steps of every batch (start() must have been called once); the last steps are left in flight."""
+        rc = self._lib.crowdsim_host_pump(len(self.steppers), self._execs, self._streams, self._events, self._dst, self._src,
+                                          self._bytes, int(rounds))
+        if rc:
+            _abi.check(rc, 'crowdsim_host_pump')
+
+    def wait(self):
+        return [s.wait() for s in self.steppers]
+
+
 def default_config(human_num=5, test_sim='circle_crossing', train_val_sim='circle_crossing', robot_visible=False,
                    randomize_attributes=False):
     """The reference's crowd_nav/configs/env.config:1-37 as a RawConfigParser (values restated, not read from disk)."""

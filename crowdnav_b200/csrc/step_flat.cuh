@@ -313,12 +313,6 @@ step_flat_kernel(const __grid_constant__ StepArgs A)
         }
     }
 
-    if constexpr (!MULTI) {
-        if (A.act_only) {                  // crowdsim_orca_act: the robot's ORCA decision only, nothing is mutated
-            if (live && is_robot) st2(A.io.action_out, e, make_double2((double)nv.x, (double)nv.y));
-            return;
-        }
-    }
     if constexpr (STAGE == 4) {            // + lp3
         if (live && !is_robot) st2(A.st.h_vel, hi, make_double2(vel.x + (double)nv.x * 0, vel.y + (double)nv.y * 0));
         return;

@@ -245,6 +245,58 @@ __global__ void __launch_bounds__(MID ? 128 : 256, MID ? CS_MID_MINBLOCKS : 1) s
 // more, less divergent warps, but were measured on B200 at 1 k .. 1 M envs and are never faster: the kernel's instruction
 // stream is almost data-independent, so sparse warps only multiply the instruction count (profiles/r01_tune_epw_n5.txt).
 
+// ---- crowdsim_orca_act for small crowds: the robot's ORCA decision only, ONE THREAD PER ENV. The step kernels' act_only mode
+// runs the whole (env, agent) lane grid for the sake of the robot lanes (5 of 30 lanes useful); a host loop that asks for the
+// robot's next decision after every step (batched.HostStepper) pays that second solve on every step. Same operations in the
+// same order as the robot lane of step_flat_kernel (neighbour_order, make_line_sel, lp1_all, lp2_scan, lp3) => same result. ----
+template <int N>
+__global__ void __launch_bounds__(128) orca_act_kernel(const __grid_constant__ StepArgs A)
+{
+    using namespace orca;
+    constexpr int M = N, T = 128;
+    __shared__ float s_l[4 * M][T], s_pj[4 * M][T];          // per-thread line / projected-line columns for linearProgram3
+    const int e = blockIdx.x * T + threadIdx.x, tid = threadIdx.x;
+    if (e >= A.B) return;
+    if (A.st.active && !A.st.active[e]) return;
+    const KParams &k = A.k;
+    const double2 pos = ld2(A.st.r_pos, e), vel = ld2(A.st.r_vel, e), goal = ld2(A.st.r_goal, e), attr = ld2(A.st.r_attr, e);
+    const double gvx = goal.x - pos.x, gvy = goal.y - pos.y;
+    const double speed = norm2(gvx, gvy);
+    const V2 pref = mk((float)((speed > 1) ? gvx / speed : gvx), (float)((speed > 1) ? gvy / speed : gvy));
+    const V2 p = mk((float)pos.x, (float)pos.y), v = mk((float)vel.x, (float)vel.y);
+    const float r = (float)(attr.x + 0.01 + k.robot_safety_space), max_speed = (float)attr.y;
+    V2 hp[M], hv[M]; float hr[M]; float dsq[M]; bool inr[M]; int id[M], src[M];
+    #pragma unroll
+    for (int c = 0; c < M; ++c) {
+        const size_t i = (size_t)e * N + c;
+        const double2 q = ld2(A.st.h_pos, i), w = ld2(A.st.h_vel, i), at = ld2(A.st.h_attr, i);
+        hp[c] = mk((float)q.x, (float)q.y); hv[c] = mk((float)w.x, (float)w.y); hr[c] = (float)(at.x + 0.01 + k.robot_safety_space);
+        dsq[c] = abssq(p - hp[c]); inr[c] = (k.max_neighbors > 0) && dsq[c] < sqr(k.neighbor_dist); id[c] = c;
+    }
+    int nl = neighbour_order<M>(dsq, inr, id, src);
+    nl = nl < k.max_neighbors ? nl : k.max_neighbors;
+    RegLines<M> R; bool valid[M];
+    #pragma unroll
+    for (int kk = 0; kk < M; ++kk) {
+        valid[kk] = kk < nl; R.p[kk] = mk(0.f, 0.f); R.d[kk] = mk(0.f, 0.f);
+        V2 qp = hp[0], qv = hv[0]; float qr = hr[0];
+        #pragma unroll
+        for (int c = 1; c < M; ++c) if (src[kk] == c) { qp = hp[c]; qv = hv[c]; qr = hr[c]; }
+        if (valid[kk]) make_line_sel(p, v, r, qp, qv, qr, k.inv_time_horizon, k.inv_time_step, R.p[kk], R.d[kk]);
+    }
+    V2 cand[M]; bool feas[M];
+    lp1_all<M, M>(R, valid, max_speed, pref, false, cand, feas);
+    V2 nv = mk(0.f, 0.f);
+    const int fail = lp2_scan<M, M>(R, valid, nl, cand, feas, lp2_init(pref, max_speed), nv);
+    if (fail < nl) {
+        const Lines Lr = { &s_l[0][tid], T }, Pr = { &s_pj[0][tid], T };
+        #pragma unroll
+        for (int kk = 0; kk < M; ++kk) Lr.set(kk, R.p[kk], R.d[kk]);
+        lp3(Lr, nl, fail, max_speed, Pr, nv);
+    }
+    st2(A.io.action_out, e, make_double2((double)nv.x, (double)nv.y));
+}
+
 // SM count of the CURRENT device (cached per device: a process may drive several GPUs).
 static int sm_count()
 {
@@ -285,6 +337,18 @@ static int launch(const crowdsim_params *prm, int B, int N, const crowdsim_state
     if (A.has_ep) A.ep = *ep; else memset(&A.ep, 0, sizeof(A.ep));
     A.has_ar = (ar != nullptr && !act_only);
     if (A.has_ar) A.ar = *ar; else memset(&A.ar, 0, sizeof(A.ar));
+    if (act_only && N >= 1 && N <= 5 && !g_force_generic) {
+        const int blocks = (B + 127) / 128;
+        switch (N) {
+            case 1: orca_act_kernel<1><<<blocks, 128, 0, stream>>>(A); break;
+            case 2: orca_act_kernel<2><<<blocks, 128, 0, stream>>>(A); break;
+            case 3: orca_act_kernel<3><<<blocks, 128, 0, stream>>>(A); break;
+            case 4: orca_act_kernel<4><<<blocks, 128, 0, stream>>>(A); break;
+            default: orca_act_kernel<5><<<blocks, 128, 0, stream>>>(A); break;
+        }
+        ++g_launches;
+        return (int)cudaGetLastError();
+    }
     if (N >= 1 && N <= 5 && !g_force_generic && !A.lookahead) {
         // small crowds: register-resident solver, 32 / (N + 1) whole envs per warp (step_flat.cuh)
         const int epb = CS_FLAT_WPB * (32 / (N + 1));
@@ -367,6 +431,25 @@ extern "C" int crowdsim_graph_launch(void *graph_exec, void *stream, void *done_
     cudaError_t e = cudaGraphLaunch((cudaGraphExec_t)graph_exec, (cudaStream_t)stream);
     if (e == cudaSuccess && done_event) e = cudaEventRecord((cudaEvent_t)done_event, (cudaStream_t)stream);
     return (int)e;
+}
+
+extern "C" int crowdsim_host_pump(int n, void *const *graph_execs, void *const *streams, void *const *events,
+                                  void *const *copy_dst, const void *const *copy_src, size_t copy_bytes, int rounds)
+{
+    // Round-robin over n independent batches (include/crowdsim_b200.h): wait for a batch's previous step, run the host-side
+    // hand-over (copy_src -> copy_dst, e.g. "apply the decision the device computed"), enqueue its next step. The same loop
+    // from an interpreter costs ~14 us per batch-step; here it is bounded by the copies and the launch call.
+    if (n < 0 || rounds < 0 || !graph_execs || !streams || !events) return CROWDSIM_EINVAL;
+    for (int r = 0; r < rounds; ++r)
+        for (int i = 0; i < n; ++i) {
+            cudaError_t e = cudaEventSynchronize((cudaEvent_t)events[i]);
+            if (e != cudaSuccess) return (int)e;
+            if (copy_bytes && copy_dst && copy_src && copy_dst[i] && copy_src[i]) memcpy(copy_dst[i], copy_src[i], copy_bytes);
+            e = cudaGraphLaunch((cudaGraphExec_t)graph_execs[i], (cudaStream_t)streams[i]);
+            if (e == cudaSuccess) e = cudaEventRecord((cudaEvent_t)events[i], (cudaStream_t)streams[i]);
+            if (e != cudaSuccess) return (int)e;
+        }
+    return CROWDSIM_OK;
 }
 
 extern "C" int crowdsim_event_wait(void *event)

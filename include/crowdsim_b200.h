@@ -215,6 +215,14 @@ void crowdsim_debug_force_generic(int on);
  * until that event has completed. No kernel of this library is launched directly by these two calls. */
 int crowdsim_graph_launch(void *graph_exec, void *stream, void *done_event);
 int crowdsim_event_wait(void *event);
+/* The round-robin of a host that keeps n independent env batches in flight, natively: `rounds` times, for every batch i:
+ * wait for events[i] (its previous step: results are in its pinned host buffers), memcpy copy_bytes from copy_src[i] to
+ * copy_dst[i] (the host-side hand-over between two steps -- e.g. next_action -> action: "apply the decision the device
+ * computed"; NULL pointers or copy_bytes = 0: none), replay graph_execs[i] on streams[i] and record events[i] behind it.
+ * On return the last step of every batch is still in flight (wait with crowdsim_event_wait). No kernel of this library is
+ * launched directly. batched.HostStepperGroup wraps it. */
+int crowdsim_host_pump(int n, void *const *graph_execs, void *const *streams, void *const *events,
+                       void *const *copy_dst, const void *const *copy_src, size_t copy_bytes, int rounds);
 
 /* One lockstep env-step for B envs. `ep` and `ar` may be NULL. */
 int crowdsim_step(const crowdsim_params *prm, int B, int N, crowdsim_state *st, crowdsim_step_io *io,

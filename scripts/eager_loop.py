@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""The bench's step / scene-prefetch sequence with EAGER launches (no CUDA graph), for ncu: same kernels, same arguments,
-same rotating batches as bench.py's timed region; ncu serialises launches anyway, so compare SHARES, not absolutes."""
+"""The bench's launch sequence with EAGER launches (no CUDA graph), for ncu: the same kernels with the same arguments as
+bench.py's timed region -- per batch one crowdsim_step_n launch of C env-steps and one scene-prefetch launch, batches rotating.
+ncu serialises launches anyway, so compare SHARES of the GPU time, not absolutes. python scripts/eager_loop.py [N] [rule] [C]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -8,18 +9,18 @@ from crowdnav_b200.batched import BatchedCrowdSim, default_config
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 rule = sys.argv[2] if len(sys.argv) > 2 else 'circle_crossing'
-B, pools, K, PE = 4096, (64 if N <= 5 else 16), 1600, 4     # PE: prefetch on every 4th visit of a batch, like bench.py
+C = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+B, pools, rounds = 4096, (64 if N <= 5 else 16), 28
 envs = []
 for p in range(pools):
     env = BatchedCrowdSim(B); env.configure(default_config(human_num=N, test_sim=rule, train_val_sim=rule)); env.set_robot_policy('orca')
-    env.k_total = 8 * B
+    env.k_total = 64 * B
     env.track_episodes(env.k_total, gamma=0.9); env.set_case_queue(p * env.k_total, env.k_total, 'train')
     env.enable_autoreset(rule); env.reset_seeds(rule=rule, use_queue=True); env.prefetch(); envs.append(env)
 torch.cuda.synchronize()
-for t in range(K):
-    env = envs[t % pools]
-    env.step()
-    if (t // pools) % PE == 0:
+for r in range(rounds):                       # rounds 24.. are in steady state (>= 192 steps per batch): profile those
+    for env in envs:
+        env.step_n(C) if C > 1 else env.step()
         env.prefetch()
 torch.cuda.synchronize()
-print('done', K)
+print('done', rounds * pools)

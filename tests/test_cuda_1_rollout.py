@@ -253,3 +253,30 @@ def test_host_stepper_batches_in_flight(cuda_env, oracle):
             steppers[q].h_action.copy_(steppers[q].h_next_action); steppers[q].launch()
     for q in range(P):
         steppers[q].wait()
+
+
+def test_host_stepper_group_native_round_robin(cuda_env, oracle):
+    """HostStepperGroup.run (crowdsim_host_pump: the round-robin in native code, device decision handed back as the next
+    action): after r rounds every batch is where r + 1 oracle steps with the ORCA decisions as actions put it."""
+    from crowdnav_b200.batched import HostStepper, HostStepperGroup
+    from crowdnav_b200 import _abi
+    B, N, P, R = 200, 5, 3, 17
+    prm_ext = oracle.default_params(robot_policy=_abi.ROBOT_EXTERNAL_XY)
+    hosts, steppers = [], []
+    for q in range(P):
+        host = oracle.HostState(B, N); oracle.reset(host, np.arange(B) + 7000 + 1000 * q)
+        env = cuda_env(B, N, robot_policy='external_xy')
+        st = HostStepper(env, next_orca_action=True, obs='f64')
+        env.state.load_host(host)
+        st.h_action.copy_(torch.from_numpy(oracle.orca_act(oracle.default_params(), host)))
+        hosts.append(host); steppers.append(st)
+    group = HostStepperGroup(steppers)
+    group.start(); group.run(R); results = group.wait()
+    for q in range(P):
+        io = oracle.HostStepIO(B)
+        for t in range(R + 1):
+            io.action[...] = oracle.orca_act(oracle.default_params(), hosts[q])
+            oracle.step(prm_ext, hosts[q], io)
+        (h_pos, h_vel), rew, done, info = results[q]
+        assert np.array_equal(h_pos.numpy(), hosts[q].h_pos) and np.array_equal(h_vel.numpy(), hosts[q].h_vel), q
+        assert np.array_equal(rew.numpy(), io.reward) and np.array_equal(info.numpy(), io.info), q
