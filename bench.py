@@ -520,7 +520,7 @@ def run_ours(args):
                 'algorithmic_bytes_per_launch': C * B * bytes_per_env, 'avg_launch_us': 1e3 * k_avg, 'env_steps_per_launch': C * B,
                 'how': 'CUDA events around each of %d replays of a single-stream graph of %d back-to-back step launches (one per rotating batch, bookkeeping + auto-reset on, scene refills between the replays untimed)' % (R, pools),
                 'single_step_kernel': {'avg_launch_us': 1e3 * k1_avg, 'achieved': B * bytes_per_env / (k1_avg * 1e-3) / 1e9,
-                                       'frac': B * bytes_per_env / (k1_avg * 1e-3) / 1e9 / peak, 'note': 'crowdsim_step (one env-step per launch), same measurement; round 1: 0.039'},
+                                       'frac': B * bytes_per_env / (k1_avg * 1e-3) / 1e9 / peak, 'note': 'crowdsim_step (one env-step per launch), same measurement (steady-state scenes, bookkeeping + auto-reset on); round 1 reported 0.039 from launches that ran past the ends of their episodes (no resets: quieter scenes)'},
                 'timed_region_GBps': (live_total / world) * bytes_per_env / (ms_max * 1e-3) / 1e9,
                 'timed_region_frac': (live_total / world) * bytes_per_env / (ms_max * 1e-3) / 1e9 / peak,
                 'timed_region_note': 'algorithmic bytes of all steps of the timed region / its duration, with %d independent batches in flight' % S}

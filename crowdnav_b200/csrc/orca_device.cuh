@@ -29,23 +29,8 @@ constexpr float kEps = 0.00001f;   // RVO_EPSILON
 
 struct V2 { float x, y; };
 ORCA_HD __forceinline__ V2 mk(float x, float y) { V2 r; r.x = x; r.y = y; return r; }
-#if defined(CS_F32X2) && defined(__CUDA_ARCH__)
-// EXPERIMENT (off by default, not measured yet -- DESIGN.md 11.2): the (x, y) arithmetic on Blackwell's packed
-// add/mul.rn.f32x2 (SASS FADD2 / FMUL2). Each half is an individually rounded IEEE binary32 operation, so results are
-// bit-identical to the scalar form; one issue slot does two operations.
-__device__ __forceinline__ unsigned long long pk(float lo, float hi) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ V2 upk(unsigned long long v) { V2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
-__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) { unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) { unsigned long long r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) { unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ V2 operator+(V2 a, V2 b) { return upk(add2(pk(a.x, a.y), pk(b.x, b.y))); }
-__device__ __forceinline__ V2 operator-(V2 a, V2 b) { return upk(sub2(pk(a.x, a.y), pk(b.x, b.y))); }
-__device__ __forceinline__ V2 operator-(V2 a) { return mk(-a.x, -a.y); }
-__device__ __forceinline__ V2 operator*(float s, V2 a) { return upk(mul2(pk(s, s), pk(a.x, a.y))); }
-__device__ __forceinline__ V2 vdiv(V2 a, float s) { const float inv = 1.0f / s; return upk(mul2(pk(a.x, a.y), pk(inv, inv))); }
-__device__ __forceinline__ float dot(V2 a, V2 b) { const V2 m = upk(mul2(pk(a.x, a.y), pk(b.x, b.y))); return m.x + m.y; }
-__device__ __forceinline__ float det(V2 a, V2 b) { const V2 m = upk(mul2(pk(a.x, a.y), pk(b.y, b.x))); return m.x - m.y; }
-#else
+// (Packed add/mul.rn.f32x2 for the (x, y) arithmetic was tried and is NOT usable under the one-rounding-per-operation contract:
+// ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under --fmad=false -- profiles/r02_f32x2_parity_fail.txt.)
 ORCA_HD __forceinline__ V2 operator+(V2 a, V2 b) { return mk(a.x + b.x, a.y + b.y); }
 ORCA_HD __forceinline__ V2 operator-(V2 a, V2 b) { return mk(a.x - b.x, a.y - b.y); }
 ORCA_HD __forceinline__ V2 operator-(V2 a) { return mk(-a.x, -a.y); }
@@ -53,7 +38,6 @@ ORCA_HD __forceinline__ V2 operator*(float s, V2 a) { return mk(s * a.x, s * a.y
 ORCA_HD __forceinline__ V2 vdiv(V2 a, float s) { const float inv = 1.0f / s; return mk(a.x * inv, a.y * inv); }
 ORCA_HD __forceinline__ float dot(V2 a, V2 b) { return a.x * b.x + a.y * b.y; }
 ORCA_HD __forceinline__ float det(V2 a, V2 b) { return a.x * b.y - a.y * b.x; }
-#endif
 ORCA_HD __forceinline__ float abssq(V2 a) { return dot(a, a); }
 ORCA_HD __forceinline__ float sqr(float a) { return a * a; }
 ORCA_HD __forceinline__ V2 normalize(V2 a) { return vdiv(a, sqrtf(abssq(a))); }
