@@ -125,7 +125,7 @@ def load():
         lib.crowdsim_graph_launch.restype = C.c_int
         lib.crowdsim_event_wait.argtypes = [C.c_void_p]
         lib.crowdsim_event_wait.restype = C.c_int
-        lib.crowdsim_host_pump.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+        lib.crowdsim_host_pump.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
         lib.crowdsim_host_pump.restype = C.c_int
         lib.crowdsim_lookahead_humans.argtypes = [C.POINTER(Params), C.c_int, C.c_int, C.POINTER(State), C.c_void_p, C.c_void_p, C.c_void_p]
         lib.crowdsim_lookahead_humans.restype = C.c_int

@@ -463,7 +463,7 @@ class HostStepper(object):
     (obs = 'f32') or self.h_pos, h_vel [B][N][2] (obs = 'f64'), h_reward, h_dmin, h_done, h_info [B], h_next_action [B][2]
     (.numpy() views are free)."""
 
-    def __init__(self, env, next_orca_action=True, obs='f32'):
+    def __init__(self, env, next_orca_action=True, obs='f32', prefetch_every=4):
         assert obs in ('f32', 'f64')
         self.env, self.obs = env, obs
         B, N, dev = env.B, env.human_num, env.device
@@ -484,10 +484,16 @@ class HostStepper(object):
         self.d2h_bytes = hi - lo
         self.kernels_per_step = 1 + (1 if env.autoreset is not None else 0) + (1 if next_orca_action else 0)
 
-        def body():
+        # The refill of the consumed next-scene slots only has to come round before the same slot's NEXT episode ends, and
+        # an episode lasts at least ~7 steps: a refill launch on every prefetch_every-th step (default 4) loses nothing, while
+        # one per step keeps 32 blocks x 78 KB of shared memory busy for ~76 us on every step of every batch in flight.
+        self.prefetch_every = max(1, int(prefetch_every))
+        self._n_launched = 0
+
+        def body(with_refill=True):
             env.action.copy_(self.h_action, non_blocking=True)
             env.step(env.action)                       # installs prefetched scenes of finished envs when auto-reset is on
-            if env.autoreset is not None:              # refill consumed slots on a side branch of the graph
+            if env.autoreset is not None and with_refill:   # refill consumed slots on a side branch of the graph
                 self.side.wait_stream(self.stream)
                 with torch.cuda.stream(self.side):
                     env.prefetch()
@@ -496,8 +502,8 @@ class HostStepper(object):
             if next_orca_action:
                 env.orca_act(env.next_action)
             hs.buf[lo:hi].copy_(env.out_slab.buf[lo:hi], non_blocking=True)
-            if env.autoreset is not None:
-                self.stream.wait_stream(self.side)     # join: the refill must be complete before the next step
+            if env.autoreset is not None and with_refill:
+                self.stream.wait_stream(self.side)     # join the side branch
         with torch.cuda.stream(self.stream):
             body()                                     # warm-up outside capture (lazy inits)
         self.stream.synchronize(); self.side.synchronize()
@@ -506,6 +512,12 @@ class HostStepper(object):
             body()
         self._lib = _abi.load()
         self._exec = self.graph.raw_cuda_graph_exec()
+        self._exec_plain = self._exec                  # the step graph without the refill branch
+        if env.autoreset is not None and self.prefetch_every > 1:
+            self.graph_plain = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_plain, stream=self.stream):
+                body(with_refill=False)
+            self._exec_plain = self.graph_plain.raw_cuda_graph_exec()
         self.done_event.record(self.stream)            # creates the underlying cudaEvent_t
         self._event_h = self.done_event.cuda_event
         self._stream_h = self.stream.cuda_stream
@@ -523,7 +535,9 @@ class HostStepper(object):
     # Both go straight to the library (crowdsim_graph_launch / crowdsim_event_wait on the raw graph-exec, stream and
     # event handles): ~3 us of interpreter time per call instead of ~12 us through torch's stream context + replay().
     def launch(self):
-        rc = self._lib.crowdsim_graph_launch(self._exec, self._stream_h, self._event_h)
+        ex = self._exec if self._n_launched % self.prefetch_every == 0 else self._exec_plain
+        self._n_launched += 1
+        rc = self._lib.crowdsim_graph_launch(ex, self._stream_h, self._event_h)
         if rc:
             _abi.check(rc, 'crowdsim_graph_launch')
 
@@ -545,6 +559,9 @@ class HostStepperGroup(object):
         n = len(self.steppers)
         arr = lambda vals: (C.c_void_p * n)(*vals)  # noqa: E731
         self._execs = arr([s._exec for s in self.steppers])
+        self._execs_plain = arr([s._exec_plain for s in self.steppers])
+        self._period = self.steppers[0].prefetch_every
+        self._round = 0
         self._streams = arr([s._stream_h for s in self.steppers])
         self._events = arr([s._event_h for s in self.steppers])
         self._dst = arr([s.h_action.data_ptr() for s in self.steppers]) if replay_next_action else None
@@ -558,8 +575,9 @@ class HostStepperGroup(object):
 
     def run(self, rounds):
         """`rounds` steps of every batch (start() must have been called once); the last steps are left in flight."""
-        rc = self._lib.crowdsim_host_pump(len(self.steppers), self._execs, self._streams, self._events, self._dst, self._src,
-                                          self._bytes, int(rounds))
+        rc = self._lib.crowdsim_host_pump(len(self.steppers), self._execs, self._execs_plain, self._period, self._round,
+                                          self._streams, self._events, self._dst, self._src, self._bytes, int(rounds))
+        self._round += int(rounds)
         if rc:
             _abi.check(rc, 'crowdsim_host_pump')
 

@@ -103,6 +103,53 @@ ORCA_HD __forceinline__ void make_line_sel(V2 p, V2 v, float r, V2 po, V2 vo, fl
     point = v + 0.5f * u;
 }
 
+// The same half-plane split for straight-line issue: make_line_far is make_line_sel's non-overlapping branch on its own (both
+// variants evaluated, selected; NO branch), make_line_overlap the already-overlapping branch. A caller evaluates make_line_far
+// for all its lines unconditionally -- the constructions are independent, so their dependent chains (2 sqrt + 2 div each)
+// interleave -- and repairs the rare overlapping lines (0.09 % of all) afterwards. For an overlapping pair make_line_far
+// computes sqrtf of a negative number (NaN); the result is discarded. Same operations per line => same bits.
+ORCA_HD __forceinline__ void make_line_far(V2 p, V2 v, float r, V2 po, V2 vo, float ro, float inv_th, V2 &point, V2 &dir, bool &overlap)
+{
+    const V2 rel_pos = po - p;
+    const V2 rel_vel = v - vo;
+    const float dist_sq = abssq(rel_pos);
+    const float comb_r = r + ro;
+    const float comb_r_sq = sqr(comb_r);
+    overlap = !(dist_sq > comb_r_sq);
+    const V2 w = rel_vel - inv_th * rel_pos;
+    const float w_len_sq = abssq(w);
+    const float dot1 = dot(w, rel_pos);
+    const float w_len = sqrtf(w_len_sq);
+    const V2 unit_w = vdiv(w, w_len);
+    const V2 dir_c = mk(unit_w.y, -unit_w.x);
+    const V2 u_c = (comb_r * inv_th - w_len) * unit_w;
+    const float leg = sqrtf(dist_sq - comb_r_sq);
+    const bool left = det(rel_pos, w) > 0.0f;
+    const V2 num_l = mk(rel_pos.x * leg - rel_pos.y * comb_r, rel_pos.x * comb_r + rel_pos.y * leg);
+    const V2 num_r = mk(rel_pos.x * leg + rel_pos.y * comb_r, -rel_pos.x * comb_r + rel_pos.y * leg);
+    const V2 q = vdiv(left ? num_l : num_r, dist_sq);
+    const V2 dir_l = left ? q : -q;
+    const float dot2 = dot(rel_vel, dir_l);
+    const V2 u_l = dot2 * dir_l - rel_vel;
+    const bool cutoff = dot1 < 0.0f && sqr(dot1) > comb_r_sq * w_len_sq;
+    dir = cutoff ? dir_c : dir_l;
+    const V2 u = cutoff ? u_c : u_l;
+    point = v + 0.5f * u;
+}
+
+ORCA_HD __forceinline__ void make_line_overlap(V2 p, V2 v, float r, V2 po, V2 vo, float ro, float inv_dt, V2 &point, V2 &dir)
+{
+    const V2 rel_pos = po - p;
+    const V2 rel_vel = v - vo;
+    const float comb_r = r + ro;
+    const V2 w = rel_vel - inv_dt * rel_pos;
+    const float w_len = sqrtf(abssq(w));
+    const V2 unit_w = vdiv(w, w_len);
+    dir = mk(unit_w.y, -unit_w.x);
+    const V2 u = (comb_r * inv_dt - w_len) * unit_w;
+    point = v + 0.5f * u;
+}
+
 // lp1 candidates of every position (speculative). valid[i]: position i holds a line (absent positions never constrain).
 // CNT = number of leading positions to evaluate (compile time, <= M).
 template <int M, int CNT>

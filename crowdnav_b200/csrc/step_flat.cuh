@@ -55,6 +55,9 @@ namespace cs {
 #ifndef CS_FLAT_MINBLOCKS
 #define CS_FLAT_MINBLOCKS 6
 #endif
+#ifndef CS_FLAT_STRAIGHT_LINES
+#define CS_FLAT_STRAIGHT_LINES 1
+#endif
 #ifndef CS_FLAT_MINBLOCKS_MULTI
 #define CS_FLAT_MINBLOCKS_MULTI 4
 #endif
@@ -182,6 +185,33 @@ step_flat_kernel(const __grid_constant__ StepArgs A)
 
     // ---- ORCA lines in rank order, in registers ----
     RegLines<M> R; bool valid[M];
+    if constexpr (CS_FLAT_STRAIGHT_LINES && MULTI) {
+        // multi-step kernel (1-2 warps per scheduler: a launch lasts as long as one warp's dependent chains): all M constructions
+        // unconditionally and branch-free, so that their chains interleave; absent positions get a far-away dummy neighbour (no
+        // special values) and are zeroed afterwards, the rare overlapping lines (0.09 %) are repaired behind a warp vote.
+        V2 qp[M], qv[M]; float qr[M]; bool ov[M]; bool any_ov = false;
+        #pragma unroll
+        for (int kk = 0; kk < M; ++kk) {
+            const int sl = ebase + src[kk];
+            const float qx = __shfl_sync(CS_FULL, fpx, sl), qy = __shfl_sync(CS_FULL, fpy, sl);
+            const float wx = __shfl_sync(CS_FULL, fvx, sl), wy = __shfl_sync(CS_FULL, fvy, sl);
+            const float rh = __shfl_sync(CS_FULL, frh, sl), rr = __shfl_sync(CS_FULL, frr, sl);
+            valid[kk] = kk < nl;
+            qp[kk] = valid[kk] ? mk(qx, qy) : mk(fpx + 100.0f, fpy); qv[kk] = valid[kk] ? mk(wx, wy) : mk(0.f, 0.f);
+            qr[kk] = valid[kk] ? (is_robot ? rr : rh) : r;
+        }
+        #pragma unroll
+        for (int kk = 0; kk < M; ++kk) {
+            make_line_far(p, v, r, qp[kk], qv[kk], qr[kk], k.inv_time_horizon, R.p[kk], R.d[kk], ov[kk]);
+            ov[kk] = ov[kk] && valid[kk]; any_ov = any_ov || ov[kk];
+        }
+        if (__any_sync(CS_FULL, any_ov)) {
+            #pragma unroll
+            for (int kk = 0; kk < M; ++kk) if (ov[kk]) make_line_overlap(p, v, r, qp[kk], qv[kk], qr[kk], k.inv_time_step, R.p[kk], R.d[kk]);
+        }
+        #pragma unroll
+        for (int kk = 0; kk < M; ++kk) if (!valid[kk]) { R.p[kk] = mk(0.f, 0.f); R.d[kk] = mk(0.f, 0.f); }
+    } else {
     #pragma unroll
     for (int kk = 0; kk < M; ++kk) {
         const int sl = ebase + src[kk];
@@ -191,6 +221,7 @@ step_flat_kernel(const __grid_constant__ StepArgs A)
         valid[kk] = kk < nl;
         R.p[kk] = mk(0.f, 0.f); R.d[kk] = mk(0.f, 0.f);
         if (valid[kk]) make_line_sel(p, v, r, mk(qx, qy), mk(wx, wy), is_robot ? rr : rh, k.inv_time_horizon, k.inv_time_step, R.p[kk], R.d[kk]);
+    }
     }
     if constexpr (STAGE == 2) {            // + preferred velocity, neighbour scan, ORCA lines
         float acc = pref.x + pref.y;

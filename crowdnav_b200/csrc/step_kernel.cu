@@ -433,7 +433,8 @@ extern "C" int crowdsim_graph_launch(void *graph_exec, void *stream, void *done_
     return (int)e;
 }
 
-extern "C" int crowdsim_host_pump(int n, void *const *graph_execs, void *const *streams, void *const *events,
+extern "C" int crowdsim_host_pump(int n, void *const *graph_execs, void *const *graph_execs_alt, int alt_period, int first_round,
+                                  void *const *streams, void *const *events,
                                   void *const *copy_dst, const void *const *copy_src, size_t copy_bytes, int rounds)
 {
     // Round-robin over n independent batches (include/crowdsim_b200.h): wait for a batch's previous step, run the host-side
@@ -445,7 +446,8 @@ extern "C" int crowdsim_host_pump(int n, void *const *graph_execs, void *const *
             cudaError_t e = cudaEventSynchronize((cudaEvent_t)events[i]);
             if (e != cudaSuccess) return (int)e;
             if (copy_bytes && copy_dst && copy_src && copy_dst[i] && copy_src[i]) memcpy(copy_dst[i], copy_src[i], copy_bytes);
-            e = cudaGraphLaunch((cudaGraphExec_t)graph_execs[i], (cudaStream_t)streams[i]);
+            const bool alt = graph_execs_alt && alt_period > 1 && ((first_round + r) % alt_period) != 0;
+            e = cudaGraphLaunch((cudaGraphExec_t)(alt ? graph_execs_alt[i] : graph_execs[i]), (cudaStream_t)streams[i]);
             if (e == cudaSuccess) e = cudaEventRecord((cudaEvent_t)events[i], (cudaStream_t)streams[i]);
             if (e != cudaSuccess) return (int)e;
         }

@@ -219,9 +219,12 @@ int crowdsim_event_wait(void *event);
  * wait for events[i] (its previous step: results are in its pinned host buffers), memcpy copy_bytes from copy_src[i] to
  * copy_dst[i] (the host-side hand-over between two steps -- e.g. next_action -> action: "apply the decision the device
  * computed"; NULL pointers or copy_bytes = 0: none), replay graph_execs[i] on streams[i] and record events[i] behind it.
+ * graph_execs_alt (may be NULL) + alt_period > 1: round number first_round + r replays graph_execs only when it is a multiple
+ * of alt_period and graph_execs_alt otherwise (e.g. the step graph with / without the scene-refill branch).
  * On return the last step of every batch is still in flight (wait with crowdsim_event_wait). No kernel of this library is
  * launched directly. batched.HostStepperGroup wraps it. */
-int crowdsim_host_pump(int n, void *const *graph_execs, void *const *streams, void *const *events,
+int crowdsim_host_pump(int n, void *const *graph_execs, void *const *graph_execs_alt, int alt_period, int first_round,
+                       void *const *streams, void *const *events,
                        void *const *copy_dst, const void *const *copy_src, size_t copy_bytes, int rounds);
 
 /* One lockstep env-step for B envs. `ep` and `ar` may be NULL. */

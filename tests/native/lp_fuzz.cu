@@ -162,6 +162,12 @@ int main(int argc, char **argv)
                 V2 lp, ld, sp, sd;
                 make_line(mk(p.x, p.y), mk(v.x, v.y), r, mk(po.x, po.y), mk(vo.x, vo.y), ro, 1.0f / 5.0f, 1.0f / 0.25f, lp, ld);
                 make_line_sel(mk(p.x, p.y), mk(v.x, v.y), r, mk(po.x, po.y), mk(vo.x, vo.y), ro, 1.0f / 5.0f, 1.0f / 0.25f, sp, sd);
+                {   // straight-line form + overlap repair (multi-step kernel)
+                    V2 fp, fd; bool ov;
+                    make_line_far(mk(p.x, p.y), mk(v.x, v.y), r, mk(po.x, po.y), mk(vo.x, vo.y), ro, 1.0f / 5.0f, fp, fd, ov);
+                    if (ov) make_line_overlap(mk(p.x, p.y), mk(v.x, v.y), r, mk(po.x, po.y), mk(vo.x, vo.y), ro, 1.0f / 0.25f, fp, fd);
+                    if (!same(fp.x, lp.x) || !same(fp.y, lp.y) || !same(fd.x, ld.x) || !same(fd.y, ld.y)) { printf("A far/overlap line mismatch\n"); return 1; }
+                }
                 if (!same(lp.x, ol[k].point.x) || !same(lp.y, ol[k].point.y) || !same(ld.x, ol[k].dir.x) || !same(ld.y, ol[k].dir.y) ||
                     !same(sp.x, lp.x) || !same(sp.y, lp.y) || !same(sd.x, ld.x) || !same(sd.y, ld.y)) { printf("A line mismatch\n"); return 1; }
                 const float dsq = po.x * po.x + po.y * po.y; cov[2] += (dsq <= (r + ro) * (r + ro));

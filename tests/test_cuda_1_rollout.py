@@ -280,3 +280,28 @@ def test_host_stepper_group_native_round_robin(cuda_env, oracle):
         (h_pos, h_vel), rew, done, info = results[q]
         assert np.array_equal(h_pos.numpy(), hosts[q].h_pos) and np.array_equal(h_vel.numpy(), hosts[q].h_vel), q
         assert np.array_equal(rew.numpy(), io.reward) and np.array_equal(info.numpy(), io.info), q
+
+
+def test_host_stepper_with_autoreset_streams_the_test_suite(cuda_env):
+    """HostStepper on an auto-resetting batch (refill branch on every 4th step only): 200 test cases streamed through 64 slots
+    with the robot driven from the host by the device's ORCA decision reproduce the reference's per-case outcomes."""
+    from crowdnav_b200.batched import HostStepper
+    cases = load_golden('suite_circle5_invisible')['cases'][:200]
+    k = len(cases)
+    env = cuda_env(64, 5, robot_policy='external_xy')
+    ep = env.track_episodes(k)
+    env.set_case_queue(0, k, 'test')
+    env.enable_autoreset()
+    stepper = HostStepper(env, next_orca_action=True, prefetch_every=4)     # its warm-up pass steps the env: start over below
+    env._case_counter.zero_(); env.autoreset.n_state.zero_(); env.autoreset.want.zero_()
+    ep.res_steps.zero_(); ep.res_info.zero_()
+    env.reset_seeds(use_queue=True); env.prefetch()
+    stepper.h_action.copy_(env.orca_act().cpu())
+    for it in range(3000):
+        stepper.step()
+        stepper.h_action.copy_(stepper.h_next_action)
+        if it % 50 == 49 and int(env.state.active.sum()) == 0 and int(env.autoreset.want.sum()) == 0:
+            break
+    assert int(env.state.active.sum()) == 0
+    assert [int(x) for x in ep.res_info.cpu()] == [c['info'] for c in cases]
+    assert [int(x) for x in ep.res_steps.cpu()] == [c['steps'] for c in cases]
