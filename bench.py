@@ -506,18 +506,19 @@ def run_ours(args):
         return tot / (R * pools)
     peak, peak_src = load_peaks()
     R = max(3, min(20, 1200 // pools))
-    k_avg = kernel_us(C)
-    k1_avg = kernel_us(1) if C > 1 else k_avg
-    achieved = C * B * bytes_per_env / (k_avg * 1e-3) / 1e9
+    CR = C if N <= 5 else 1                                  # env-steps of ONE kernel launch (N > 5: crowdsim_step_n = n launches of the crowd kernel)
+    k_avg = kernel_us(CR)
+    k1_avg = kernel_us(1) if CR > 1 else k_avg
+    achieved = CR * B * bytes_per_env / (k_avg * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'step_traffic.json')
     if os.path.exists(tpath) and N == 5 and B == 4096:
         tj = json.load(open(tpath))
-        if tj.get('steps_per_launch', 1) == C:
+        if tj.get('steps_per_launch', 1) == CR:
             traffic = tj['dram_bytes_read'] + tj['dram_bytes_write']      # from the committed ncu --set full capture, per launch
-    roofline = {'bound': 'hbm', 'kernel': ('cs::step_flat_kernel<%d, MULTI> (crowdsim_step_n, %d env-steps per launch)' % (N, C)) if N <= 5 and C > 1 else ('cs::step_flat_kernel' if N <= 5 else 'cs::step_kernel'),
+    roofline = {'bound': 'hbm', 'kernel': ('cs::step_flat_kernel<%d, MULTI> (crowdsim_step_n, %d env-steps per launch)' % (N, CR)) if N <= 5 and CR > 1 else ('cs::step_flat_kernel' if N <= 5 else 'cs::step_kernel<MID> (crowd kernel, step_mid.cuh)'),
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
-                'algorithmic_bytes_per_launch': C * B * bytes_per_env, 'avg_launch_us': 1e3 * k_avg, 'env_steps_per_launch': C * B,
+                'algorithmic_bytes_per_launch': CR * B * bytes_per_env, 'avg_launch_us': 1e3 * k_avg, 'env_steps_per_launch': CR * B,
                 'how': 'CUDA events around each of %d replays of a single-stream graph of %d back-to-back step launches (one per rotating batch, bookkeeping + auto-reset on, scene refills between the replays untimed)' % (R, pools),
                 'single_step_kernel': {'avg_launch_us': 1e3 * k1_avg, 'achieved': B * bytes_per_env / (k1_avg * 1e-3) / 1e9,
                                        'frac': B * bytes_per_env / (k1_avg * 1e-3) / 1e9 / peak, 'note': 'crowdsim_step (one env-step per launch), same measurement (steady-state scenes, bookkeeping + auto-reset on); round 1 reported 0.039 from launches that ran past the ends of their episodes (no resets: quieter scenes)'},

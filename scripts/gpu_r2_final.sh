@@ -5,6 +5,15 @@ echo "== pytest -m gpu -x -q (the driver's command)"; timeout 1800 python -m pyt
 echo "== smoke"; timeout 600 python __graft_entry__.py --smoke 2>&1 | tail -3 | tee gpurun_out/r2_final_smoke.txt
 echo "== reference arm (driver flags)"; timeout 900 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02_bench_reference_arm.json 2>gpurun_out/bench_ref.err || tail -5 gpurun_out/bench_ref.err
 echo "== bench (driver flags)"; timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02_bench_n1_final.json 2>gpurun_out/bench.err || tail -20 gpurun_out/bench.err
+echo "== bench, BASELINE config 4 (20 humans, square crossing)"; timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 --humans 20 --rule square_crossing --no-cpu-baseline --no-scale > gpurun_out/r02_bench_cfg4_n1.json 2>gpurun_out/bench4.err || tail -5 gpurun_out/bench4.err
+python - <<'PY'
+import json
+try:
+    d = json.loads(open('gpurun_out/r02_bench_cfg4_n1.json').read().strip().splitlines()[-1])
+    print('config 4: value %.1fM single %.1fM roofline %s %.2f us/launch frac %.4f e2e %.1fM' % (d['value']/1e6, d['single_batch']['value']/1e6, d['roofline']['kernel'], d['roofline']['avg_launch_us'], d['roofline']['frac'], d['e2e']['value']/1e6))
+except Exception as e:
+    print('config 4 bench unreadable', e)
+PY
 echo "== configs 1/3/4"; timeout 900 python scripts/measure_misc.py > gpurun_out/r02_configs_1_3_4.json 2>gpurun_out/misc.err || tail -5 gpurun_out/misc.err
 python - <<'PY'
 import json
