@@ -44,9 +44,11 @@ namespace cs {
 // attribute latency); the library only instantiates the full kernel (STAGE = 99).
 // Register budget of the single-step kernel: 6 resident blocks per SM (<= 80 registers) is neutral at 4096 envs and 9 %
 // faster at 65 k .. 1 M envs than the unconstrained build (round 1); the multi-step kernel serves launches that leave
-// the chip mostly empty and carries ~35 registers of state across steps: 4 blocks per SM (<= 128 registers, no spills).
+// the chip mostly empty and carries ~35 registers of state across steps: 4 blocks per SM (<= 128 registers).
 // Measured through bench.py (profiles/r02_multi_regs.txt): 3 / 4 / 5 blocks per SM = 131 / 128 / 96 registers give 790 / 848 /
 // 878 M env-steps/s with 16 batches in flight and 390 / 399 / 389 M for a single batch: 4 is the balance.
+// CS_FLAT_STRAIGHT_LINES (multi-step kernel): the M line constructions unconditionally and branch-free so that their chains
+// interleave (profiles/r02_multi_straight_lines.txt: launch 72.9 -> 71.5 us); 0 = the branchy form of the single-step kernel.
 // ROT: the robot is a unicycle (CROWDSIM_ROBOT_EXTERNAL_ROT, agent.py:115-135). A template parameter so that the double
 // precision cos / sin / fmod code (12 % of the round-1 kernel's SASS) is only present in the kernels that execute it.
 #ifndef CS_FLAT_WPB
