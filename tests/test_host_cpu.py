@@ -489,3 +489,30 @@ def test_cadrl_and_lstm_rl_policy_logic_matches_reference(oracle, key):
         top2 = np.sort(ref)[-2:]
         if top2[1] - top2[0] > 1e-4:
             assert [float(x) for x in r['action']] == [float(x) for x in act[e]], (key, e)
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference (the CPU arm the driver runs next to ours): one JSON line with the contract's keys, the thread
+    calibration bounded by the usable CPUs, a sane rate; and the sizing of the timed region of our arm (whole rounds, a multiple
+    of K, >= 200 replays for short K)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--envs', '256', '--steps', '5', '--warmup', '3',
+                          '--no-python-loop'], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-1000:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d['impl'] == 'reference' and d['unit'] == 'env-steps/s' and d['higher_is_better'] is True and d['steps'] == 5
+    assert d['value'] > 1e5 and d['e2e']['value'] == d['value'] and d['e2e']['h2d_bytes_per_step'] == 0
+    cb = d['cpu_baseline']
+    assert cb['kind'] == 'port' and 1 <= cb['cores'] <= len(os.sched_getaffinity(0))
+    assert str(cb['cores']) in cb['calibration_env_steps_per_s'] and d['gpu_launches'] == 0
+    sys.path.insert(0, root)
+    import bench
+    assert bench._lcm(20, 512) == 2560 and bench._lcm(25600, 512) == 25600
+    for K in (20, 7, 1000, 25600):
+        unit = bench._lcm(K, 512)
+        want = max(200 * K if K <= 4096 else K, 40000)
+        timed = (want + unit - 1) // unit * unit
+        assert timed % K == 0 and timed % 512 == 0 and timed // K >= (200 if K <= 4096 else 1)
