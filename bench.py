@@ -50,6 +50,7 @@ def parse():
     ap.add_argument('--streams', type=int, default=16, help='independent env batches stepped concurrently (CUDA streams inside the timed graph)')
     ap.add_argument('--e2e-batches', type=int, default=16, help='independent env batches kept in flight by the e2e leg')
     ap.add_argument('--e2e-obs', default='f32', choices=['f32', 'f64'], help='observation format of the e2e leg (HostStepper obs=)')
+    ap.add_argument('--e2e-transfer', default='direct', choices=['direct', 'copy'], help="how the e2e leg's host buffers cross the link: the kernels load / store pinned host memory themselves, or copy-engine transfers")
     ap.add_argument('--chunk', type=int, default=8, help='env-steps per launch (crowdsim_step_n); 1 = one launch per step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-python-loop', action='store_true', help='reference arm: skip the reference-shaped Python loop timing')
@@ -560,7 +561,7 @@ def run_ours(args):
     for env in envs[:P]:
         env.reset_seeds(rule=args.rule, use_queue=True)      # fresh scenes (the step-only pass ran past terminal states)
         env.set_robot_policy('external_xy')
-        steppers.append(HostStepper(env, next_orca_action=True, obs=args.e2e_obs))
+        steppers.append(HostStepper(env, next_orca_action=True, obs=args.e2e_obs, transfer=args.e2e_transfer if args.e2e_obs == 'f32' else 'copy'))
     for st in steppers:
         st.step()
         for _ in range(40):                                  # into the episodes
@@ -652,7 +653,7 @@ def run_ours(args):
                               'note': 'value = performed / time; performed is counted by the step kernel (episode step counters), nominal = envs x steps; they differ only if envs waited for a scene refill'},
                 'clocks': clocks, 'gpu_launches': int(launches), 'gpu_launches_note': launches_note,
                 'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                        'steps': 2 * ke, 'batches_in_flight': P, 'single_batch_blocking': e2e_single, 'python_round_robin': e2e_python, 'observation': args.e2e_obs,
+                        'steps': 2 * ke, 'batches_in_flight': P, 'transfer': steppers[0].transfer, 'single_batch_blocking': e2e_single, 'python_round_robin': e2e_python, 'observation': args.e2e_obs,
                         'note': 'HostStepperGroup.run() (round-robin in native code: crowdsim_host_pump; python_round_robin = the same loop written in Python with HostStepper.launch()/wait()) over %d independent %d-env batches: per batch-step a pinned host action buffer goes up and obs (%s)/reward/dmin/done/info/next ORCA action come down (byte counts are per batch-step), the host waits for a batch\'s results before it feeds that batch again; single_batch_blocking = one batch, host blocks on every step' % (P, B, 'float32 px,py,vx,vy per human' if args.e2e_obs == 'f32' else 'float64 state arrays')},
                 'single_batch': single, 'parity_500_cases': parity, 'episodes': episodes, 'roofline': roofline, 'scale': scale, 'cpu_baseline': cpu}
         print(json.dumps(line))

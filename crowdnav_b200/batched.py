@@ -461,11 +461,17 @@ class HostStepper(object):
     obs = 'f64': the float64 state arrays themselves, 210 B per env.
     Buffers: self.h_action [B][2] (write before step()); results as views of the pinned host slab: self.h_obs32 [B][N][4]
     (obs = 'f32') or self.h_pos, h_vel [B][N][2] (obs = 'f64'), h_reward, h_dmin, h_done, h_info [B], h_next_action [B][2]
-    (.numpy() views are free)."""
+    (.numpy() views are free).
+    transfer = 'copy' (default): the buffers cross the link with copy-engine transfers (one up, one down per step).
+    transfer = 'direct': the kernels read the action from, and write the step's results to, the pinned host buffers
+    themselves (unified addressing: the same pointers are valid on the device) -- the same bytes cross the link on every
+    step, but as loads / stores of the step and decision kernels instead of two DMA transfers with their fixed set-up cost;
+    the results are visible to the host once the step's event has completed (wait())."""
 
-    def __init__(self, env, next_orca_action=True, obs='f32', prefetch_every=4):
-        assert obs in ('f32', 'f64')
-        self.env, self.obs = env, obs
+    def __init__(self, env, next_orca_action=True, obs='f32', prefetch_every=4, transfer='copy'):
+        assert obs in ('f32', 'f64') and transfer in ('copy', 'direct')
+        assert transfer == 'copy' or obs == 'f32', "transfer='direct' serves the float32 observation"
+        self.env, self.obs, self.transfer = env, obs, transfer
         B, N, dev = env.B, env.human_num, env.device
         self.h_action = torch.zeros((B, 2), dtype=torch.float64).pin_memory()
         self.host_slab = Slab(host_visible_layout(B, N), 'cpu', pin=True)
@@ -482,6 +488,8 @@ class HostStepper(object):
             lo, hi = hs.offsets['reward'][0], hs.offsets['h_vel'][0] + hs.offsets['h_vel'][1]
         self.h2d_bytes = self.h_action.numel() * 8
         self.d2h_bytes = hi - lo
+        if transfer == 'direct':                      # what the kernels store to host memory per step
+            self.d2h_bytes = B * (N * 16 + 8 + 8 + 1 + 1 + (16 if next_orca_action else 0))
         self.kernels_per_step = 1 + (1 if env.autoreset is not None else 0) + (1 if next_orca_action else 0)
 
         # The refill of the consumed next-scene slots only has to come round before the same slot's NEXT episode ends, and
@@ -490,8 +498,15 @@ class HostStepper(object):
         self.prefetch_every = max(1, int(prefetch_every))
         self._n_launched = 0
 
+        direct = transfer == 'direct'
+        if direct:
+            # the env's per-step inputs / outputs now ARE the pinned host buffers (device-visible through unified addressing)
+            env.action, env.obs32, env.reward, env.dmin = self.h_action, self.h_obs32, self.h_reward, self.h_dmin
+            env.done, env.info, env.next_action, env.action_out = self.h_done, self.h_info, self.h_next_action, None
+
         def body(with_refill=True):
-            env.action.copy_(self.h_action, non_blocking=True)
+            if not direct:
+                env.action.copy_(self.h_action, non_blocking=True)
             env.step(env.action)                       # installs prefetched scenes of finished envs when auto-reset is on
             if env.autoreset is not None and with_refill:   # refill consumed slots on a side branch of the graph
                 self.side.wait_stream(self.stream)
@@ -501,7 +516,8 @@ class HostStepper(object):
             # was measured: 47 M vs 54 M env-steps/s -- the extra stream hand-offs cost more than the overlap gains.)
             if next_orca_action:
                 env.orca_act(env.next_action)
-            hs.buf[lo:hi].copy_(env.out_slab.buf[lo:hi], non_blocking=True)
+            if not direct:
+                hs.buf[lo:hi].copy_(env.out_slab.buf[lo:hi], non_blocking=True)
             if env.autoreset is not None and with_refill:
                 self.stream.wait_stream(self.side)     # join the side branch
         with torch.cuda.stream(self.stream):

@@ -193,12 +193,12 @@ def test_explorer_case_range_wraps_like_the_reference(cuda_env):
     assert env.case_counter['test'] == 15
 
 
-@pytest.mark.parametrize('obs,N', [('f64', 5), ('f32', 5), ('f32', 8)])
-def test_host_stepper_matches_oracle(cuda_env, oracle, obs, N):
+@pytest.mark.parametrize('obs,N,transfer', [('f64', 5, 'copy'), ('f32', 5, 'copy'), ('f32', 8, 'copy'), ('f32', 5, 'direct'), ('f32', 8, 'direct')])
+def test_host_stepper_matches_oracle(cuda_env, oracle, obs, N, transfer):
     """The host-facing step API (pinned buffers in/out, one CUDA graph per call): driving the robot from the host with the
     'next action' the device computed reproduces the oracle's ORCA-robot episodes bit-exactly, array for array. obs='f32':
     the compact observation (crowdsim_step_io.obs32, small-crowd and generic kernel) is the float32 cast of the oracle's
-    float64 state, exactly."""
+    float64 state, exactly. transfer='direct': the kernels read / write the pinned host buffers themselves (no copy nodes)."""
     from crowdnav_b200.batched import HostStepper
     from crowdnav_b200 import _abi
     B = 300
@@ -206,7 +206,7 @@ def test_host_stepper_matches_oracle(cuda_env, oracle, obs, N):
     oracle.reset(host, np.arange(B) + 1000)
     env = cuda_env(B, N, robot_policy='external_xy')
     env.state.load_host(host)
-    stepper = HostStepper(env, next_orca_action=True, obs=obs)   # its warm-up + capture passes step the env: reload the scene
+    stepper = HostStepper(env, next_orca_action=True, obs=obs, transfer=transfer)   # its warm-up + capture passes step the env: reload the scene
     env.state.load_host(host)
     prm_ext = oracle.default_params(robot_policy=_abi.ROBOT_EXTERNAL_XY)
     act = oracle.orca_act(oracle.default_params(), host)
