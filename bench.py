@@ -50,7 +50,7 @@ def parse():
     ap.add_argument('--streams', type=int, default=16, help='independent env batches stepped concurrently (CUDA streams inside the timed graph)')
     ap.add_argument('--e2e-batches', type=int, default=16, help='independent env batches kept in flight by the e2e leg')
     ap.add_argument('--e2e-obs', default='f32', choices=['f32', 'f64'], help='observation format of the e2e leg (HostStepper obs=)')
-    ap.add_argument('--e2e-transfer', default='direct', choices=['direct', 'copy'], help="how the e2e leg's host buffers cross the link: the kernels load / store pinned host memory themselves, or copy-engine transfers")
+    ap.add_argument('--e2e-transfer', default='auto', choices=['auto', 'direct', 'copy'], help="how the e2e leg's host buffers cross the link: the kernels load / store pinned host memory themselves (better for 4096-env batches: 3.0e8 vs 2.8e8), or copy-engine transfers (better for 16384-env batches: 3.96e8 vs 3.6e8 per GPU); auto = by the bytes per step")
     ap.add_argument('--chunk', type=int, default=8, help='env-steps per launch (crowdsim_step_n); 1 = one launch per step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-python-loop', action='store_true', help='reference arm: skip the reference-shaped Python loop timing')
@@ -561,7 +561,8 @@ def run_ours(args):
     for env in envs[:P]:
         env.reset_seeds(rule=args.rule, use_queue=True)      # fresh scenes (the step-only pass ran past terminal states)
         env.set_robot_policy('external_xy')
-        steppers.append(HostStepper(env, next_orca_action=True, obs=args.e2e_obs, transfer=args.e2e_transfer if args.e2e_obs == 'f32' else 'copy'))
+        e2e_transfer = args.e2e_transfer if args.e2e_transfer != 'auto' else ('direct' if B * (16 * N + 34) < (1 << 20) else 'copy')
+        steppers.append(HostStepper(env, next_orca_action=True, obs=args.e2e_obs, transfer=e2e_transfer if args.e2e_obs == 'f32' else 'copy'))
     for st in steppers:
         st.step()
         for _ in range(40):                                  # into the episodes
