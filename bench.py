@@ -51,7 +51,7 @@ def parse():
     ap.add_argument('--e2e-batches', type=int, default=16, help='independent env batches kept in flight by the e2e leg')
     ap.add_argument('--e2e-obs', default='f32', choices=['f32', 'f64'], help='observation format of the e2e leg (HostStepper obs=)')
     ap.add_argument('--e2e-transfer', default='auto', choices=['auto', 'direct', 'copy'], help="how the e2e leg's host buffers cross the link: the kernels load / store pinned host memory themselves (better for 4096-env batches: 3.0e8 vs 2.8e8), or copy-engine transfers (better for 16384-env batches: 3.96e8 vs 3.6e8 per GPU); auto = by the bytes per step")
-    ap.add_argument('--chunk', type=int, default=8, help='env-steps per launch (crowdsim_step_n); 1 = one launch per step')
+    ap.add_argument('--chunk', type=int, default=16, help='env-steps per launch (crowdsim_step_n); 1 = one launch per step. 8 / 12 / 16 / 24 give 839 / 866 / 905 / 883 M env-steps/s (24: 6 %% of the env-steps lost to envs waiting for a scene refill)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-python-loop', action='store_true', help='reference arm: skip the reference-shaped Python loop timing')
     ap.add_argument('--no-scale', action='store_true', help='skip the supplementary 1 Mi-env launch measurement')
