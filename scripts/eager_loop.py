@@ -9,8 +9,8 @@ from crowdnav_b200.batched import BatchedCrowdSim, default_config
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 rule = sys.argv[2] if len(sys.argv) > 2 else 'circle_crossing'
-C = int(sys.argv[3]) if len(sys.argv) > 3 else 8
-B, pools, rounds = 4096, (64 if N <= 5 else 16), 28
+C = int(sys.argv[3]) if len(sys.argv) > 3 else 16
+B, pools, rounds = 4096, (64 if N <= 5 else 16), 28      # (profiles/r02_launch_list_* and r02_step_n_4096envs_* were captured with C = 8)
 envs = []
 for p in range(pools):
     env = BatchedCrowdSim(B); env.configure(default_config(human_num=N, test_sim=rule, train_val_sim=rule)); env.set_robot_policy('orca')
